@@ -1,0 +1,333 @@
+// rvq_aux.cu -- the HBM-bound helpers around the fused encode kernel:
+//   K0  codebook operand preparation (fp16 scaled copy, scaled norms, per-stage metadata)
+//   K3  EMA finalize (count/sum decay, Laplace smoothing, codebook refresh)
+//   dequantize (code lookup summed over stages)
+//   exact-scan encode (every code scored in fp32 on CUDA cores; verification / RVQ_ALGO_EXACT_SCAN)
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "exact.cuh"
+
+namespace rvq {
+
+// ------------------------------------------------------------------------------------------ K0
+// one block per stage: max |c| over the valid codes -> meta[q] = {2^b, 0 (cnmax, filled by k0_convert), cmax, Kv}
+__global__ void k0_stage_max(const float* __restrict__ cb, const int* __restrict__ k_valid, int K, int d,
+                             float* __restrict__ meta) {
+    const int q = blockIdx.x;
+    const int Kv = k_valid ? min(max(k_valid[q], 0), K) : K;
+    const float* base = cb + (size_t)q * K * d;
+    const size_t n = (size_t)Kv * d;
+    float m = 0.f;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(base[i]));
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) {
+            float* mq = meta + q * META_STRIDE;
+            mq[0] = exp2i(code_scale_exp(m));
+            mq[1] = 0.f;
+            mq[2] = m;
+            mq[3] = (float)Kv;
+            mq[4] = mq[5] = mq[6] = mq[7] = 0.f;
+        }
+    }
+}
+
+// one warp per (stage, padded code row): fp16 operand row, scaled norm, running max of ||c||_2
+__global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad, int d, __half* __restrict__ op,
+                           float* __restrict__ norm, float* __restrict__ meta) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nq * Kpad) return;
+    const int q = warp / Kpad, k = warp % Kpad;
+    float* mq = meta + q * META_STRIDE;
+    const float sb = mq[0];
+    const int Kv = (int)mq[3];
+    __half* orow = op + ((size_t)q * Kpad + k) * d;
+    if (k >= Kv) {
+        for (int i = lane; i < d; i += 32) orow[i] = __float2half_rn(0.f);
+        if (lane == 0) norm[(size_t)q * Kpad + k] = PAD_NORM;
+        return;
+    }
+    const float* crow = cb + ((size_t)q * K + k) * d;
+    float nrm = 0.f;
+    const float m2sb = -2.f * sb;
+    for (int i = lane; i < d; i += 32) {
+        const float c = crow[i];
+        nrm = fmaf(c, c, nrm);
+        orow[i] = __float2half_rn(c * m2sb);  // exact power-of-two scaling, one fp16 rounding
+    }
+    for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    if (lane == 0) {
+        norm[(size_t)q * Kpad + k] = nrm * sb * sb;
+        // upper bound of ||c||_2 (fp32 summation slack) ; positive floats order like ints
+        const float cn = sqrtf(nrm) * (1.f + 1e-5f);
+        atomicMax(reinterpret_cast<int*>(mq + 1), __float_as_int(cn));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+// one block per stage: EMA of the counts and n_tot = sum_k ema_count (written to scratch[q])
+__global__ void k3_counts(float* __restrict__ ema_count, const float* __restrict__ cnt, const int* __restrict__ k_valid,
+                          int K, float decay, float omd, float* __restrict__ ntot) {
+    const int q = blockIdx.x;
+    const int Kv = k_valid ? min(max(k_valid[q], 0), K) : K;
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < Kv; k += blockDim.x) {
+        const size_t i = (size_t)q * K + k;
+        const float v = __fadd_rn(__fmul_rn(decay, ema_count[i]), __fmul_rn(omd, cnt[i]));
+        ema_count[i] = v;
+        acc += v;
+    }
+    __shared__ float red[32];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) ntot[q] = acc;
+    }
+}
+
+// one warp per (stage, code): EMA of the sums and the smoothed codebook refresh
+__global__ void k3_codes(float* __restrict__ cb, const float* __restrict__ ema_count, float* __restrict__ ema_sum,
+                         const float* __restrict__ sum, const int* __restrict__ k_valid, const float* __restrict__ ntot,
+                         int nq, int K, int d, float decay, float omd, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= nq * K) return;
+    const int q = warp / K, k = warp % K;
+    const int Kv = k_valid ? min(max(k_valid[q], 0), K) : K;
+    if (k >= Kv) return;
+    const float n = ntot[q];
+    const float smoothed = __fmul_rn(__fdiv_rn(__fadd_rn(ema_count[(size_t)q * K + k], eps),
+                                               __fadd_rn(n, __fmul_rn((float)Kv, eps))), n);
+    const size_t base = ((size_t)q * K + k) * d;
+    for (int i = lane * 4; i < d; i += 128) {
+        float4 es = *reinterpret_cast<const float4*>(ema_sum + base + i);
+        const float4 sv = *reinterpret_cast<const float4*>(sum + base + i);
+        es.x = __fadd_rn(__fmul_rn(decay, es.x), __fmul_rn(omd, sv.x));
+        es.y = __fadd_rn(__fmul_rn(decay, es.y), __fmul_rn(omd, sv.y));
+        es.z = __fadd_rn(__fmul_rn(decay, es.z), __fmul_rn(omd, sv.z));
+        es.w = __fadd_rn(__fmul_rn(decay, es.w), __fmul_rn(omd, sv.w));
+        *reinterpret_cast<float4*>(ema_sum + base + i) = es;
+        float4 cv;
+        cv.x = __fdiv_rn(es.x, smoothed);
+        cv.y = __fdiv_rn(es.y, smoothed);
+        cv.z = __fdiv_rn(es.z, smoothed);
+        cv.w = __fdiv_rn(es.w, smoothed);
+        *reinterpret_cast<float4*>(cb + base + i) = cv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ dequantize
+struct RowAddr {
+    long long L, sb, sl, sd;
+    __device__ __forceinline__ long long row(long long n) const { return (n / L) * sb + (n % L) * sl; }
+};
+
+__global__ void dequantize_rows(const float* __restrict__ cb, const long long* __restrict__ idx, long long N,
+                                RowAddr ad, int d, int q0, int nq, int K, float4 w0, const float* __restrict__ w,
+                                int accumulate, float* __restrict__ out) {
+    // one warp per frame when features are contiguous, else frames-fastest scalar mapping
+    if (ad.sd == 1) {
+        const long long n = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        if (n >= N) return;
+        float* o = out + ad.row(n);
+        for (int i = lane * 4; i < d; i += 128) {
+            float4 acc = accumulate ? *reinterpret_cast<const float4*>(o + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < nq; ++q) {
+                long long k = idx[n * nq + q];
+                k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+                const float4 c = *reinterpret_cast<const float4*>(cb + ((size_t)(q0 + q) * K + k) * d + i);
+                const float wq = w ? w[q] : 1.f;
+                acc.x = fmaf(wq, c.x, acc.x);
+                acc.y = fmaf(wq, c.y, acc.y);
+                acc.z = fmaf(wq, c.z, acc.z);
+                acc.w = fmaf(wq, c.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(o + i) = acc;
+        }
+    } else {
+        const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long long total = N * d;
+        if (t >= total) return;
+        const long long chunk = 128;  // frames-fastest inside groups of 128 frames
+        const long long g = t / (chunk * d), rem = t % (chunk * d);
+        const int i = (int)(rem / chunk);
+        const long long n = g * chunk + rem % chunk;
+        if (n >= N) return;
+        float* o = out + ad.row(n) + (long long)i * ad.sd;
+        float acc = accumulate ? *o : 0.f;
+        for (int q = 0; q < nq; ++q) {
+            long long k = idx[n * nq + q];
+            k = k < 0 ? 0 : (k >= K ? K - 1 : k);
+            acc = fmaf(w ? w[q] : 1.f, cb[((size_t)(q0 + q) * K + k) * d + i], acc);
+        }
+        *o = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ exact-scan encode
+// One warp per frame; the residual lives in shared memory; every code of every stage is scored with
+// exact_score8.  Slow (CUDA cores) but it is the semantic definition the tensor path must reproduce.
+__global__ void __launch_bounds__(256) encode_exact_scan(const float* __restrict__ x, long long N, RowAddr ad, int d,
+                                                         int nq, int K, const float* __restrict__ cb,
+                                                         const float* __restrict__ meta, float* __restrict__ xq,
+                                                         long long* __restrict__ idx, double* __restrict__ commit_sq,
+                                                         float* __restrict__ stats_sum, float* __restrict__ stats_cnt) {
+    extern __shared__ __align__(16) float smem_r[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (n >= N) return;
+    float* r = smem_r + (size_t)warp * d;
+    const float* xr = x + ad.row(n);
+    for (int i = lane; i < d; i += 32) r[i] = xr[(long long)i * ad.sd];
+    __syncwarp();
+    for (int q = 0; q < nq; ++q) {
+        const float* cbq = cb + (size_t)q * K * d;
+        const int Kv = (int)meta[q * META_STRIDE + 3];
+        ScoreIdx best = exact_scan_warp(r, cbq, d, 0, Kv, lane);
+        int kw = best.k;
+        if (kw < 0 || kw >= Kv) kw = 0;
+        const float* cw = cbq + (size_t)kw * d;
+        float sq = 0.f;
+        for (int i = lane * 4; i < d; i += 128) {
+            const float4 rv = *reinterpret_cast<const float4*>(r + i);
+            const float4 cv = ldg_nc_v4(cw + i);
+            if (stats_sum) red_add_v4(stats_sum + ((size_t)q * K + kw) * d + i, rv);
+            float4 nr;
+            nr.x = rv.x - cv.x;
+            nr.y = rv.y - cv.y;
+            nr.z = rv.z - cv.z;
+            nr.w = rv.w - cv.w;
+            *reinterpret_cast<float4*>(r + i) = nr;
+            sq = fmaf(nr.x, nr.x, sq);
+            sq = fmaf(nr.y, nr.y, sq);
+            sq = fmaf(nr.z, nr.z, sq);
+            sq = fmaf(nr.w, nr.w, sq);
+        }
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) {
+            idx[n * nq + q] = kw;
+            atomicAdd(commit_sq + q, (double)sq);
+            if (stats_cnt) atomicAdd(stats_cnt + (size_t)q * K + kw, 1.f);
+        }
+        __syncwarp();
+    }
+    float* xo = xq + ad.row(n);
+    for (int i = lane; i < d; i += 32) xo[(long long)i * ad.sd] = xr[(long long)i * ad.sd] - r[i];
+}
+
+}  // namespace rvq
+
+// ------------------------------------------------------------------------------------------ host wrappers
+using namespace rvq;
+
+extern "C" int rvq_prepared_bytes(int nq, int K, int d, size_t* op_bytes, size_t* norm_bytes, size_t* meta_bytes) {
+    if (nq <= 0 || K <= 0 || d <= 0) {
+        set_error("rvq_prepared_bytes: nq, K, d must be positive (got %d, %d, %d)", nq, K, d);
+        return RVQ_ERR_ARG;
+    }
+    const size_t Kpad = round_up(K, CHUNK_N);
+    if (op_bytes) *op_bytes = (size_t)nq * Kpad * d * sizeof(__half);
+    if (norm_bytes) *norm_bytes = (size_t)nq * Kpad * sizeof(float);
+    if (meta_bytes) *meta_bytes = (size_t)nq * META_STRIDE * sizeof(float);
+    return RVQ_OK;
+}
+
+int rvq_check_shape(const char* who, int nq, int K, int d) {
+    if (nq <= 0 || K <= 0 || d <= 0 || d > MAX_D || d % KSLICE != 0) {
+        set_error("%s: unsupported shape nq=%d K=%d d=%d (need nq,K >= 1 and d a multiple of %d, <= %d)", who, nq, K, d,
+                  KSLICE, MAX_D);
+        return RVQ_ERR_ARG;
+    }
+    return RVQ_OK;
+}
+
+extern "C" int rvq_prepare_codebooks(const float* cb, const int* k_valid, int nq, int K, int d, void* cb_op,
+                                     float* cb_norm, float* cb_meta, void* stream) {
+    if (int e = rvq_check_shape("rvq_prepare_codebooks", nq, K, d)) return e;
+    if (!cb || !cb_op || !cb_norm || !cb_meta) {
+        set_error("rvq_prepare_codebooks: null pointer");
+        return RVQ_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Kpad = round_up(K, CHUNK_N);
+    k0_stage_max<<<nq, 1024, 0, st>>>(cb, k_valid, K, d, cb_meta);
+    const long long warps = (long long)nq * Kpad;
+    const int block = 256;
+    const long long grid = (warps * 32 + block - 1) / block;
+    k0_convert<<<(unsigned)grid, block, 0, st>>>(cb, nq, K, Kpad, d, static_cast<__half*>(cb_op), cb_norm, cb_meta);
+    RVQ_CUDA(cudaGetLastError());
+    return RVQ_OK;
+}
+
+extern "C" int rvq_ema_finalize(float* cb, float* ema_count, float* ema_sum, const float* stats_sum,
+                                const float* stats_cnt, const int* k_valid, int nq_use, int K, int d, float decay,
+                                float eps, void* stream) {
+    if (int e = rvq_check_shape("rvq_ema_finalize", nq_use, K, d)) return e;
+    if (!cb || !ema_count || !ema_sum || !stats_sum || !stats_cnt) {
+        set_error("rvq_ema_finalize: null pointer");
+        return RVQ_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // n_tot scratch: a small stream-ordered allocation (nq floats)
+    float* ntot = nullptr;
+    RVQ_CUDA(cudaMallocAsync(&ntot, sizeof(float) * nq_use, st));
+    const float omd = (float)(1.0 - (double)decay);
+    k3_counts<<<nq_use, 1024, 0, st>>>(ema_count, stats_cnt, k_valid, K, decay, omd, ntot);
+    const long long warps = (long long)nq_use * K;
+    const int block = 256;
+    k3_codes<<<(unsigned)((warps * 32 + block - 1) / block), block, 0, st>>>(cb, ema_count, ema_sum, stats_sum, k_valid,
+                                                                             ntot, nq_use, K, d, decay, omd, eps);
+    RVQ_CUDA(cudaGetLastError());
+    RVQ_CUDA(cudaFreeAsync(ntot, st));
+    return RVQ_OK;
+}
+
+extern "C" int rvq_dequantize(const float* cb, const long long* idx, long long N, long long L, long long stride_b,
+                              long long stride_l, long long stride_d, int d, int q0, int nq_use, int K, const float* w,
+                              int accumulate, float* out, void* stream) {
+    if (int e = rvq_check_shape("rvq_dequantize", nq_use, K, d)) return e;
+    if (!cb || !idx || !out || N < 0 || L <= 0 || q0 < 0) {
+        set_error("rvq_dequantize: bad argument");
+        return RVQ_ERR_ARG;
+    }
+    if (N == 0) return RVQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* wdev = nullptr;
+    if (w) {
+        RVQ_CUDA(cudaMallocAsync(&wdev, sizeof(float) * nq_use, st));
+        RVQ_CUDA(cudaMemcpyAsync(wdev, w, sizeof(float) * nq_use, cudaMemcpyHostToDevice, st));
+    }
+    RowAddr ad{L, stride_b, stride_l, stride_d};
+    const int block = 256;
+    const long long threads = stride_d == 1 ? N * 32 : ((N + 127) / 128) * 128 * d;
+    dequantize_rows<<<(unsigned)((threads + block - 1) / block), block, 0, st>>>(cb, idx, N, ad, d, q0, nq_use, K,
+                                                                                 make_float4(0, 0, 0, 0), wdev,
+                                                                                 accumulate, out);
+    RVQ_CUDA(cudaGetLastError());
+    if (wdev) RVQ_CUDA(cudaFreeAsync(wdev, st));
+    return RVQ_OK;
+}
+
+// called from rvq_encode (rvq_abi.cu)
+int rvq_launch_exact_scan(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d,
+                          int nq, int K, const float* cb, const float* meta, float* xq, long long* idx,
+                          double* commit_sq, float* stats_sum, float* stats_cnt, cudaStream_t st) {
+    RowAddr ad{L, sb, sl, sd};
+    const int block = 256, rows = block / 32;
+    const size_t smem = (size_t)rows * d * sizeof(float);
+    encode_exact_scan<<<(unsigned)((N + rows - 1) / rows), block, smem, st>>>(x, N, ad, d, nq, K, cb, meta, xq, idx,
+                                                                              commit_sq, stats_sum, stats_cnt);
+    RVQ_CUDA(cudaGetLastError());
+    return RVQ_OK;
+}

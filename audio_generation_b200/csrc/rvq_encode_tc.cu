@@ -1,0 +1,679 @@
+// rvq_encode_tc.cu -- K1 (+K2 fused): the residual-vector-quantization stage loop as ONE persistent
+// sm_100a kernel.  Replaces the per-stage {distance, argmin, gather, subtract, EMA statistics} loop of
+// som_quantizer.ResidualQuantizer.forward (called at /root/reference/networks/vae.py:315-318).
+//
+// Per CTA (one per SM, persistent over 128-frame tiles), per stage q:
+//   filter   scores~[128 x K] = (2^a r) . (-2 * 2^b C_q)^T on tcgen05 (fp16 operands, fp32 accumulate in
+//            TMEM, 256 codes per accumulator buffer, two buffers), B streamed by TMA through an mbarrier ring;
+//            the residual operand A is produced by the CTA itself in the UMMA SWIZZLE_128B K-major layout.
+//   argmin   epilogue warps read the accumulators with tcgen05.ld, add 2^(a-b) * (2^(2b)||c||^2) and keep the
+//            three smallest packed (score | column) values per frame; nothing N x K ever reaches HBM.
+//   certify  every code whose approximate score is within delta = 2 * (proven fp16 error bound) of the best is
+//            re-scored exactly in fp32 (exact.cuh); if the third best is also inside delta the frame falls
+//            back to an exact scan of all K codes.  The selected index is therefore the exact fp32 argmin.
+//   update   r <- r - C_q[k] in fp32 (residual tile resident in shared memory for d <= 128, else in an
+//            L2-resident per-CTA scratch), EMA statistics by red.global.add.v4.f32, commit-loss partials,
+//            next stage's fp16 operand written back into the A tile.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 / 8-11 = epilogue groups 0 / 1 (accumulator buffers 0 / 1).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "exact.cuh"
+
+namespace rvq {
+
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int MAX_STAGES_RING = 6;
+constexpr int MAX_NQ = 64;
+constexpr uint32_t A_SLICE_BYTES = TILE_M * KSLICE * 2;   // 16 KiB
+constexpr uint32_t B_STAGE_BYTES = CHUNK_N * KSLICE * 2;  // 32 KiB
+constexpr uint32_t BAR_EPI = 1;                           // named barrier id for the 256 epilogue threads
+constexpr float BIG = 3.0e38f;
+
+struct RowAddrT {
+    long long L, sb, sl, sd;
+    __device__ __forceinline__ long long row(long long n) const { return (n / L) * sb + (n % L) * sl; }
+};
+
+struct EncParams {
+    const float* x;
+    long long N;
+    RowAddrT ad;
+    int d, nq, K, Kpad, q_begin;
+    const float* cb;       // [*, K, d] fp32 master
+    const float* cb_norm;  // [*, Kpad] scaled norms
+    const float* cb_meta;  // [*, 8]
+    float* xq;
+    long long* idx;
+    double* commit_sq;
+    float* stats_sum;
+    float* stats_cnt;
+    float* r_scratch;  // per-CTA [128, d] fp32 when the residual tile does not fit in shared memory
+    int num_tiles, nstage, r_in_smem, r_pitch;
+    uint32_t off_B, off_R, off_misc;  // A tile at offset 0
+    float* dbg_scores;                // [128, Kpad] (bring-up hook) or null
+    float* dbg_rowscale;              // [128] or null
+};
+
+struct __align__(16) Misc {
+    uint64_t full[MAX_STAGES_RING], empty[MAX_STAGES_RING], tmem_full[2], tmem_empty[2], a_ready;
+    uint32_t tmem_base;
+    int dirty_count;
+    float row_na[TILE_M], row_delta[TILE_M];
+    int cand1[TILE_M], cand2[TILE_M], ncand[TILE_M];
+    float mrg_v[3][TILE_M];
+    int mrg_k[2][TILE_M];
+    int dirty_rows[TILE_M];
+    float dirty_s[8];
+    int dirty_k[8];
+    double commit_acc[MAX_NQ];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// residual tile access: element (row, col) -> float*
+struct RTile {
+    float* base;
+    int pitch;
+    __device__ __forceinline__ float* at(int row, int col) const { return base + (size_t)row * pitch + col; }
+};
+
+// byte offset of fp16 element (row, col) inside the A tile (d/64 slices of [128 rows x 128 B], SWIZZLE_128B)
+__device__ __forceinline__ uint32_t a_tile_offset(int row, int col) {
+    const int slice = col >> 6, c = col & 63;
+    return (uint32_t)slice * A_SLICE_BYTES + (uint32_t)row * 128u + ((((uint32_t)c >> 3) ^ ((uint32_t)row & 7u)) << 4) +
+           (((uint32_t)c & 7u) << 1);
+}
+
+// An 8-lane group finishes one frame of one stage: optional r <- r - c_win (+ EMA statistics), squared norm
+// and max of the new residual, the per-row constants and the fp16 operand row of the NEXT stage.
+// All 32 lanes of the warp must call this together (8-lane shuffles with a full mask); `active` gates effects.
+//   kwin < 0      : stage-0 initialisation (no subtraction)
+//   next_stage<0  : last stage (no operand for a next stage)
+__device__ __forceinline__ void finish_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int row,
+                                           bool active, bool row_valid, int kwin, int q_abs, int next_q_abs, int sub,
+                                           float* sq_out) {
+    const int d = p.d;
+    float sq = 0.f, amax = 0.f;
+    if (active) {
+        if (kwin >= 0) {
+            const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d;
+            float* ssum = (p.stats_sum && row_valid) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d : nullptr;
+            for (int c = sub * 4; c < d; c += 32) {
+                float4 rv = *reinterpret_cast<float4*>(rt.at(row, c));
+                const float4 cv = ldg_nc_v4(cw + c);
+                if (ssum) red_add_v4(ssum + c, rv);
+                rv.x -= cv.x;
+                rv.y -= cv.y;
+                rv.z -= cv.z;
+                rv.w -= cv.w;
+                *reinterpret_cast<float4*>(rt.at(row, c)) = rv;
+                sq = fmaf(rv.x, rv.x, sq);
+                sq = fmaf(rv.y, rv.y, sq);
+                sq = fmaf(rv.z, rv.z, sq);
+                sq = fmaf(rv.w, rv.w, sq);
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(rv.x), fabsf(rv.y)), fmaxf(fabsf(rv.z), fabsf(rv.w))));
+            }
+        } else {
+            for (int c = sub * 4; c < d; c += 32) {
+                const float4 rv = *reinterpret_cast<float4*>(rt.at(row, c));
+                sq = fmaf(rv.x, rv.x, sq);
+                sq = fmaf(rv.y, rv.y, sq);
+                sq = fmaf(rv.z, rv.z, sq);
+                sq = fmaf(rv.w, rv.w, sq);
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(rv.x), fabsf(rv.y)), fmaxf(fabsf(rv.z), fabsf(rv.w))));
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    }
+    if (sq_out) *sq_out = sq;
+    if (!active || next_q_abs < 0) return;
+
+    // ---- constants + fp16 operand row for the next stage
+    const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
+    const float sb = mq[0];        // 2^b
+    const float cnmax = mq[1];     // max ||c||_2 (upper bound)
+    const int b = ilog2f_floor(sb);
+    int a = b + ROW_OVER_CODE_MAX;
+    bool force_exact = !isfinite(amax) || !isfinite(sq);
+    if (amax > 0.f && isfinite(amax)) a = min(a, SCALE_TARGET_EXP - ilog2f_floor(amax));
+    if (a < b - ROW_UNDER_CODE_MAX) force_exact = true;  // frame >= 2^40 x larger than the codes: no fp16 window
+    a = max(a, b - ROW_UNDER_CODE_MAX);
+    a = max(-100, min(100, a));
+    const float sa = exp2i(a);
+    if (sub == 0) {
+        const float na = exp2i(max(-120, min(120, a - b)));
+        const float rs = sqrtf(sq) * 1.00002f * sa;  // scaled ||r||_2 (upper bound)
+        const float cs = cnmax * sb;                 // scaled max ||c||_2
+        // |approx - exact| (scaled units) <= 2^-9(1+..) rs cs  [fp16 rounding of both operands, Cauchy-Schwarz]
+        //   + 2^-15 |score|                                   [8 low mantissa bits replaced by the column]
+        //   + d 2^-14                                          [fp16 subnormal absolute error, accumulate slack]
+        const float E = 1.02f * 0.001953125f * rs * cs + 3.0517578125e-5f * (na * cs * cs + 2.f * rs * cs) +
+                        (float)d * 6.103515625e-5f;
+        float delta = 2.1f * E;
+        if (force_exact || !isfinite(delta)) delta = __int_as_float(0x7f800000);
+        misc->row_na[row] = na;
+        misc->row_delta[row] = delta;
+        if (p.dbg_rowscale) p.dbg_rowscale[row] = sa;
+    }
+    for (int c = sub * 4; c < d; c += 32) {
+        const float4 rv = *reinterpret_cast<float4*>(rt.at(row, c));
+        const __half2 h01 = __floats2half2_rn(rv.x * sa, rv.y * sa);
+        const __half2 h23 = __floats2half2_rn(rv.z * sa, rv.w * sa);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+        *reinterpret_cast<uint2*>(smem_a + a_tile_offset(row, c)) = pk;
+    }
+}
+
+__device__ __forceinline__ bool less_vk(float v, int k, float bv, int bk) { return (v < bv) || (v == bv && k < bk); }
+
+// running best-two (value, code) and third value of one frame
+struct Top3 {
+    float v1, v2, v3;
+    int k1, k2;
+    __device__ __forceinline__ void reset() {
+        v1 = v2 = v3 = BIG;
+        k1 = k2 = 0x7fffffff;
+    }
+    __device__ __forceinline__ void insert(float v, int k) {
+        if (less_vk(v, k, v1, k1)) {
+            v3 = v2;
+            v2 = v1;
+            k2 = k1;
+            v1 = v;
+            k1 = k;
+        } else if (less_vk(v, k, v2, k2)) {
+            v3 = v2;
+            v2 = v;
+            k2 = k;
+        } else {
+            v3 = fminf(v3, v);
+        }
+    }
+};
+
+template <bool kDebug>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + p.off_B;
+    Misc* misc = reinterpret_cast<Misc*>(smem + p.off_misc);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = p.d, nq = p.nq;
+    const int n_ks = d / KSLICE;
+    const int n_chunks = p.Kpad / CHUNK_N;
+    const int nstage = p.nstage;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstage; ++i) {
+            mbar_init(&misc->full[i], 1);
+            mbar_init(&misc->empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&misc->tmem_full[i], 1);
+            mbar_init(&misc->tmem_empty[i], 4);  // one arrive per epilogue warp of the group
+        }
+        mbar_init(&misc->a_ready, 1);
+        misc->dirty_count = 0;
+        for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_b);
+    if (warp == 2) tmem_alloc<512>(&misc->tmem_base);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = misc->tmem_base;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer (codebook slices)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int q = 0; q < nq; ++q) {
+                    const int row0 = (p.q_begin + q) * p.Kpad;
+                    for (int c = 0; c < n_chunks; ++c) {
+                        for (int ks = 0; ks < n_ks; ++ks, ++it) {
+                            const uint32_t s = it % nstage, ph = (it / nstage) & 1;
+                            mbar_wait(&misc->empty[s], ph ^ 1);
+                            mbar_arrive_expect_tx(&misc->full[s], B_STAGE_BYTES);
+                            tma_load_2d(smem_b + (size_t)s * B_STAGE_BYTES, &tmap_b, &misc->full[s], ks * KSLICE,
+                                        row0 + c * CHUNK_N);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer
+        const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CHUNK_N);
+        uint32_t it = 0, g = 0, astage = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int q = 0; q < nq; ++q) {
+                mbar_wait(&misc->a_ready, astage & 1);
+                ++astage;
+                tc_fence_after_sync();
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const uint32_t buf = g & 1, use = g >> 1;
+                    mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
+                    tc_fence_after_sync();
+                    const uint32_t tmem_d = tmem_base + buf * CHUNK_N;
+                    for (int ks = 0; ks < n_ks; ++ks, ++it) {
+                        const uint32_t s = it % nstage, ph = (it / nstage) & 1;
+                        mbar_wait(&misc->full[s], ph);
+                        tc_fence_after_sync();
+                        if (lane == 0) {
+                            const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)ks * A_SLICE_BYTES));
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)s * B_STAGE_BYTES));
+#pragma unroll
+                            for (int k16 = 0; k16 < KSLICE / 16; ++k16) {
+                                // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
+                                umma_f16_ss(tmem_d, adesc + (uint64_t)(k16 * 2), bdesc + (uint64_t)(k16 * 2), idesc,
+                                            (ks | k16) != 0);
+                            }
+                            umma_commit(&misc->empty[s]);  // frees the ring slot when these MMAs retire
+                            if (ks == n_ks - 1) umma_commit(&misc->tmem_full[buf]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // =========================================================== epilogue groups
+        const int e = threadIdx.x - EPI_WARP0 * 32;  // 0..255
+        const int grp = e >> 7;                      // epilogue group = accumulator buffer
+        const int my_row = (warp & 3) * 32 + lane;   // TMEM lane owned by this thread
+        const int sub = e & 7, slot = e >> 3;        // 8-lane groups for the cooperative phase
+        const int ewarp = e >> 5;                    // 0..7
+        RTile rt;
+        if (p.r_in_smem) {
+            rt.base = reinterpret_cast<float*>(smem + p.off_R);
+        } else {
+            rt.base = p.r_scratch + (size_t)blockIdx.x * TILE_M * p.r_pitch;
+        }
+        rt.pitch = p.r_pitch;
+        const bool row_major = (p.ad.sd == 1);
+        uint32_t g = 0;
+
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const long long n0 = (long long)tile * TILE_M;
+            // ---------------- load the frame tile into the residual buffer
+            if (row_major) {
+                for (int pass = 0; pass < TILE_M / 32; ++pass) {
+                    const int row = pass * 32 + slot;
+                    const long long n = n0 + row;
+                    const float* xr = p.x + (n < p.N ? p.ad.row(n) : 0);
+                    for (int c = sub * 4; c < d; c += 32) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (n < p.N) v = *reinterpret_cast<const float4*>(xr + c);
+                        *reinterpret_cast<float4*>(rt.at(row, c)) = v;
+                    }
+                }
+            } else {
+                const int row = e & (TILE_M - 1);
+                const long long n = n0 + row;
+                const float* xr = p.x + (n < p.N ? p.ad.row(n) : 0);
+                for (int c = e >> 7; c < d; c += EPI_THREADS / TILE_M) {
+                    *rt.at(row, c) = (n < p.N) ? xr[(long long)c * p.ad.sd] : 0.f;
+                }
+            }
+            named_bar_sync(BAR_EPI, EPI_THREADS);
+            for (int pass = 0; pass < TILE_M / 32; ++pass) {
+                const int row = pass * 32 + slot;
+                finish_row(p, misc, smem_a, rt, row, true, n0 + row < p.N, -1, 0, p.q_begin, sub, nullptr);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(BAR_EPI, EPI_THREADS);
+            if (e == 0) mbar_arrive(&misc->a_ready);
+
+            for (int q = 0; q < nq; ++q) {
+                const int q_abs = p.q_begin + q;
+                const float na = misc->row_na[my_row];
+                const float delta = misc->row_delta[my_row];
+                const float* nrm_q = p.cb_norm + (size_t)q_abs * p.Kpad;
+                Top3 G;
+                G.reset();
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    if ((int)(g & 1) != grp) continue;
+                    mbar_wait(&misc->tmem_full[grp], (g >> 1) & 1);
+                    tc_fence_after_sync();
+                    float m1 = BIG, m2 = BIG, m3 = BIG;
+                    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CHUNK_N;
+#pragma unroll 1
+                    for (int cb32 = 0; cb32 < CHUNK_N / 32; ++cb32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr + cb32 * 32, v);
+                        tmem_ld_wait();
+                        const float* nptr = nrm_q + c * CHUNK_N + cb32 * 32;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 nn = __ldg(reinterpret_cast<const float4*>(nptr + j));
+                            const float nv[4] = {nn.x, nn.y, nn.z, nn.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float s = fmaf(na, nv[t], __uint_as_float(v[j + t]));
+                                if constexpr (kDebug) v[j + t] = __float_as_uint(s);
+                                const float pk =
+                                    __uint_as_float((__float_as_uint(s) & 0xFFFFFF00u) | (uint32_t)(cb32 * 32 + j + t));
+                                const float t_ = fmaxf(m1, pk);
+                                m1 = fminf(m1, pk);
+                                const float u_ = fmaxf(m2, t_);
+                                m2 = fminf(m2, t_);
+                                m3 = fminf(m3, u_);
+                            }
+                        }
+                        if (kDebug && p.dbg_scores && tile == 0 && q == 0) {
+                            float* o = p.dbg_scores + (size_t)my_row * p.Kpad + c * CHUNK_N + cb32 * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+                        }
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&misc->tmem_empty[grp]);
+                    // chunk-local best three -> running best of the stage (values with the column bits cleared)
+                    const uint32_t b1 = __float_as_uint(m1), b2 = __float_as_uint(m2), b3 = __float_as_uint(m3);
+                    G.insert(__uint_as_float(b1 & 0xFFFFFF00u), c * CHUNK_N + (int)(b1 & 0xFFu));
+                    G.insert(__uint_as_float(b2 & 0xFFFFFF00u), c * CHUNK_N + (int)(b2 & 0xFFu));
+                    G.v3 = fminf(G.v3, __uint_as_float(b3 & 0xFFFFFF00u));
+                }
+                // ---------------- merge the two groups' candidates, decide how many need an exact score
+                if (grp == 1) {
+                    misc->mrg_v[0][my_row] = G.v1;
+                    misc->mrg_v[1][my_row] = G.v2;
+                    misc->mrg_v[2][my_row] = G.v3;
+                    misc->mrg_k[0][my_row] = G.k1;
+                    misc->mrg_k[1][my_row] = G.k2;
+                }
+                named_bar_sync(BAR_EPI, EPI_THREADS);
+                if (grp == 0) {
+                    G.insert(misc->mrg_v[0][my_row], misc->mrg_k[0][my_row]);
+                    G.insert(misc->mrg_v[1][my_row], misc->mrg_k[1][my_row]);
+                    G.v3 = fminf(G.v3, misc->mrg_v[2][my_row]);
+                    const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
+                    int nc;
+                    const float lim = G.v1 + delta;
+                    if (!(G.v1 < BIG) || G.k1 >= Kv || !(lim == lim)) {
+                        nc = 3;  // no usable filter result (NaN / overflow): exact scan
+                    } else if (G.v2 > lim) {
+                        nc = 1;
+                    } else if (G.v3 > lim && G.k2 < Kv) {
+                        nc = 2;
+                    } else {
+                        nc = 3;
+                    }
+                    misc->cand1[my_row] = G.k1;
+                    misc->cand2[my_row] = G.k2;
+                    misc->ncand[my_row] = nc;
+                    if (nc == 3) {
+                        const int pos = atomicAdd(&misc->dirty_count, 1);
+                        misc->dirty_rows[pos] = my_row;
+                    }
+                }
+                named_bar_sync(BAR_EPI, EPI_THREADS);
+
+                // ---------------- cooperative phase: exact re-rank, gather, residual update, statistics
+                const int next_q_abs = (q + 1 < nq) ? q_abs + 1 : -1;
+                const float* cbq = p.cb + (size_t)q_abs * p.K * d;
+                for (int pass = 0; pass < TILE_M / 32; ++pass) {
+                    const int row = pass * 32 + slot;
+                    const long long n = n0 + row;
+                    const int nc = misc->ncand[row];
+                    int k1 = misc->cand1[row], k2 = misc->cand2[row];
+                    int kwin = k1;
+                    if (__any_sync(0xffffffffu, nc == 2)) {
+                        if (nc != 2) k1 = k2 = 0;
+                        const float s1 = exact_score8(rt.at(row, 0), cbq + (size_t)k1 * d, d, sub);
+                        const float s2 = exact_score8(rt.at(row, 0), cbq + (size_t)k2 * d, d, sub);
+                        if (nc == 2 && better(s2, k2, s1, k1)) kwin = k2;
+                    }
+                    const bool active = nc != 3;
+                    float sq;
+                    finish_row(p, misc, smem_a, rt, row, active, n < p.N, active ? kwin : 0, q_abs, next_q_abs, sub,
+                               &sq);
+                    if (active && sub == 0 && n < p.N) {
+                        p.idx[n * nq + q] = kwin;
+                        atomicAdd(&misc->commit_acc[q], (double)sq);
+                        if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
+                    }
+                }
+                // ---------------- frames the filter could not certify: exact scan of every code
+                const int n_dirty = misc->dirty_count;  // stable: written before the last barrier
+                if (n_dirty > 0) {
+                    const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
+                    const int per = (Kv + 7) / 8;
+                    for (int i = 0; i < n_dirty; ++i) {
+                        const int row = misc->dirty_rows[i];
+                        const int k0 = min(Kv, ewarp * per), k1 = min(Kv, k0 + per);
+                        const ScoreIdx b = exact_scan_warp(rt.at(row, 0), cbq, d, k0, k1, lane);
+                        if (lane == 0) {
+                            misc->dirty_s[ewarp] = b.s;
+                            misc->dirty_k[ewarp] = b.k;
+                        }
+                        named_bar_sync(BAR_EPI, EPI_THREADS);
+                        if (ewarp == (i & 7)) {
+                            float bs = misc->dirty_s[0];
+                            int bk = misc->dirty_k[0];
+                            for (int w = 1; w < 8; ++w)
+                                if (better(misc->dirty_s[w], misc->dirty_k[w], bs, bk)) {
+                                    bs = misc->dirty_s[w];
+                                    bk = misc->dirty_k[w];
+                                }
+                            if (bk < 0 || bk >= Kv) bk = 0;
+                            const long long n = n0 + row;
+                            float sq;
+                            finish_row(p, misc, smem_a, rt, row, lane < 8, n < p.N, bk, q_abs, next_q_abs, sub, &sq);
+                            if (lane == 0 && n < p.N) {
+                                p.idx[n * nq + q] = bk;
+                                atomicAdd(&misc->commit_acc[q], (double)sq);
+                                if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + bk, 1.f);
+                            }
+                        }
+                        named_bar_sync(BAR_EPI, EPI_THREADS);
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(BAR_EPI, EPI_THREADS);
+                if (e == 0) {
+                    misc->dirty_count = 0;
+                    if (next_q_abs >= 0) mbar_arrive(&misc->a_ready);
+                }
+            }
+            // ---------------- xq = x - final residual
+            if (row_major) {
+                for (int pass = 0; pass < TILE_M / 32; ++pass) {
+                    const int row = pass * 32 + slot;
+                    const long long n = n0 + row;
+                    if (n < p.N) {
+                        const long long off = p.ad.row(n);
+                        for (int c = sub * 4; c < d; c += 32) {
+                            const float4 xv = *reinterpret_cast<const float4*>(p.x + off + c);
+                            const float4 rv = *reinterpret_cast<const float4*>(rt.at(row, c));
+                            float4 o;
+                            o.x = xv.x - rv.x;
+                            o.y = xv.y - rv.y;
+                            o.z = xv.z - rv.z;
+                            o.w = xv.w - rv.w;
+                            *reinterpret_cast<float4*>(p.xq + off + c) = o;
+                        }
+                    }
+                }
+            } else {
+                const int row = e & (TILE_M - 1);
+                const long long n = n0 + row;
+                if (n < p.N) {
+                    const long long off = p.ad.row(n);
+                    for (int c = e >> 7; c < d; c += EPI_THREADS / TILE_M) {
+                        const long long o = off + (long long)c * p.ad.sd;
+                        p.xq[o] = p.x[o] - *rt.at(row, c);
+                    }
+                }
+            }
+            named_bar_sync(BAR_EPI, EPI_THREADS);  // residual buffer is reused by the next tile
+        }
+        if (e < nq) {
+            const double v = misc->commit_acc[e];
+            if (v != 0.0) atomicAdd(p.commit_sq + e, v);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace rvq
+
+// ------------------------------------------------------------------------------------------ host side
+using namespace rvq;
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+struct SmemPlan {
+    uint32_t off_B, off_R, off_misc, total;
+    int nstage, r_in_smem, r_pitch;
+};
+
+SmemPlan plan_smem(int d, int smem_max) {
+    SmemPlan s{};
+    const uint32_t a_bytes = (uint32_t)(d / KSLICE) * A_SLICE_BYTES;
+    const uint32_t misc_bytes = (uint32_t)((sizeof(Misc) + 1023) / 1024 * 1024);
+    const uint32_t r_bytes_smem = (uint32_t)TILE_M * (d + 4) * 4;
+    const uint32_t r_aligned = (r_bytes_smem + 1023) / 1024 * 1024;
+    // residual tile in shared memory only if at least 3 ring stages still fit
+    s.r_in_smem = (a_bytes + r_aligned + misc_bytes + 3 * B_STAGE_BYTES + 1024 <= (uint32_t)smem_max) ? 1 : 0;
+    s.r_pitch = s.r_in_smem ? d + 4 : d;
+    s.off_B = a_bytes;
+    const uint32_t fixed = a_bytes + (s.r_in_smem ? r_aligned : 0) + misc_bytes + 1024;
+    int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / B_STAGE_BYTES) : 0;
+    if (ns > MAX_STAGES_RING) ns = MAX_STAGES_RING;
+    s.nstage = ns;
+    s.off_R = s.off_B + (uint32_t)ns * B_STAGE_BYTES;
+    s.off_misc = s.off_R + (s.r_in_smem ? r_aligned : 0);
+    s.total = s.off_misc + misc_bytes + 1024;  // slack for the 1024-byte alignment of the dynamic base
+    return s;
+}
+}  // namespace
+
+int rvq_tc_workspace_bytes(int d, int num_sms, size_t* out) {
+    // per-CTA residual scratch (used when the tile does not fit in shared memory)
+    *out = (size_t)num_sms * TILE_M * d * sizeof(float) + 256;
+    return RVQ_OK;
+}
+
+int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d, int nq,
+                  int K, int q_begin, const float* cb, const void* cb_op, int nq_total, const float* cb_norm,
+                  const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
+                  float* stats_cnt, void* ws, size_t ws_bytes, float* dbg_scores, float* dbg_rowscale,
+                  cudaStream_t st) {
+    if (nq > MAX_NQ) {
+        set_error("rvq_encode: at most %d stages are supported (got %d)", MAX_NQ, nq);
+        return RVQ_ERR_ARG;
+    }
+    int dev = 0, num_sms = 0, smem_max = 0;
+    RVQ_CUDA(cudaGetDevice(&dev));
+    RVQ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    RVQ_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int Kpad = round_up(K, CHUNK_N);
+    const SmemPlan sp = plan_smem(d, smem_max);
+    if (sp.nstage < 2) {
+        set_error("rvq_encode: d=%d leaves no room for the codebook ring in %d bytes of shared memory", d, smem_max);
+        return RVQ_ERR_ARG;
+    }
+    EncodeTiledFn encode = get_encode_tiled();
+    if (!encode) {
+        set_error("rvq_encode: cuTensorMapEncodeTiled is not available from the driver");
+        return RVQ_ERR_CUDA;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nq_total * Kpad};
+    const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)CHUNK_N};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(cb_op), gdim, gstride, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("rvq_encode: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        return RVQ_ERR_CUDA;
+    }
+    const int num_tiles = (int)((N + TILE_M - 1) / TILE_M);
+    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+    EncParams p{};
+    p.x = x;
+    p.N = N;
+    p.ad = RowAddrT{L, sb, sl, sd};
+    p.d = d;
+    p.nq = nq;
+    p.K = K;
+    p.Kpad = Kpad;
+    p.q_begin = q_begin;
+    p.cb = cb;
+    p.cb_norm = cb_norm;
+    p.cb_meta = cb_meta;
+    p.xq = xq;
+    p.idx = idx;
+    p.commit_sq = commit_sq;
+    p.stats_sum = stats_sum;
+    p.stats_cnt = stats_cnt;
+    p.num_tiles = num_tiles;
+    p.nstage = sp.nstage;
+    p.r_in_smem = sp.r_in_smem;
+    p.r_pitch = sp.r_pitch;
+    p.off_B = sp.off_B;
+    p.off_R = sp.off_R;
+    p.off_misc = sp.off_misc;
+    p.dbg_scores = dbg_scores;
+    p.dbg_rowscale = dbg_rowscale;
+    if (!sp.r_in_smem) {
+        const size_t need = (size_t)grid * TILE_M * d * sizeof(float);
+        uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
+        if (!ws || base + need > reinterpret_cast<uintptr_t>(ws) + ws_bytes) {
+            set_error("rvq_encode: workspace too small (%zu bytes given, %zu needed)", ws_bytes, need + 256);
+            return RVQ_ERR_WORKSPACE;
+        }
+        p.r_scratch = reinterpret_cast<float*>(base);
+    }
+    if (dbg_scores) {
+        RVQ_CUDA(cudaFuncSetAttribute(rvq_encode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sp.total));
+        rvq_encode_tc_kernel<true><<<grid, NUM_THREADS, sp.total, st>>>(tmap, p);
+    } else {
+        RVQ_CUDA(cudaFuncSetAttribute(rvq_encode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sp.total));
+        rvq_encode_tc_kernel<false><<<grid, NUM_THREADS, sp.total, st>>>(tmap, p);
+    }
+    RVQ_CUDA(cudaGetLastError());
+    return RVQ_OK;
+}

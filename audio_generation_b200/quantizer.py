@@ -1,0 +1,321 @@
+"""Host-side mirror of the reference's quantizer interface, on the sm_100a kernels.
+
+Drop-in for ``som_quantizer.ResidualQuantizer`` (third-party quantization-maps package imported at
+``/root/reference/networks/vae.py:6``): same constructor keywords (``vae.py:245-251``), same call and
+return order ``(x_quantized, index, commit_loss)`` (``vae.py:315-318``), same attributes the reference
+reads (``.num_quantizers`` ``training.py:183``, ``.use_som`` ``utils.py:239``, ``.quantizers[i].dequantize``
+``vae.py:333``, ``.quantizers[i].som.height/.width`` ``utils.py:244-245``, ``.get_stale_clusters()``
+``training.py:435``, ``.update_cutoff()`` ``vae.py:350-351``).
+
+PyTorch owns every tensor (device memory, streams, ``torch.distributed``); all arithmetic of the path
+runs in ``librvq_sm100a.so`` through the C ABI of ``include/rvq_sm100a.h``.  There is no CPU path:
+a CPU tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import RVQError, RVQ_ALGO_EXACT_SCAN, RVQ_ALGO_TENSOR
+
+EMA_DECAY = 0.99   # ASSUMED (rosinality / Jukebox lineage, README.md:26-27)
+EMA_EPS = 1e-5     # ASSUMED
+
+
+def tuple_checker(item, length):
+    """Same behaviour as ``/root/reference/networks/utils.py:212-220``."""
+    if isinstance(item, (int, float, str)):
+        item = [item] * length
+    elif isinstance(item, (tuple, list)):
+        assert len(item) == length, f"Expected tuple of length {length}, got {len(item)}"
+    return item
+
+
+def approximate_square_root(n: int):
+    h = int(math.isqrt(int(n)))
+    while h > 1 and n % h:
+        h -= 1
+    return h, n // h
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _frame_addressing(x: torch.Tensor):
+    """(x3, N, L, stride_b, stride_l, stride_d) for a (..., L, d) tensor; copies only when the layout
+    cannot be addressed as base + b*sb + l*sl + i*sd with a dense, non-overlapping footprint."""
+    if x.dim() == 2:
+        x3 = x.unsqueeze(0)
+    elif x.dim() == 3:
+        x3 = x
+    else:
+        x3 = x.reshape(-1, x.shape[-2], x.shape[-1])
+    ok = x3.is_contiguous() or x3.transpose(1, 2).is_contiguous()
+    if ok and x3.stride(2) == 1:
+        ok = (x3.stride(1) % 4 == 0) and (x3.stride(0) % 4 == 0) and (x3.data_ptr() % 16 == 0)
+    if not ok:
+        x3 = x3.contiguous()
+    B, L, _ = x3.shape
+    return x3, B * L, L, x3.stride(0), x3.stride(1), x3.stride(2)
+
+
+class _SOMGrid:
+    """Grid shape of the self-organising map attached to a stage (``utils.py:244-245,257``)."""
+
+    def __init__(self, K: int):
+        self.height, self.width = approximate_square_root(K)
+
+
+class _Stage:
+    """``ResidualQuantizer.quantizers[i]``: one stage's view of the shared state."""
+
+    def __init__(self, parent: "ResidualQuantizer", q: int):
+        self._p, self._q = parent, q
+        if parent.use_som:
+            self.som = _SOMGrid(parent.codebook_sizes[q])
+
+    @property
+    def codebook(self) -> torch.Tensor:
+        return self._p.codebooks[self._q, : self._p.codebook_sizes[self._q]]
+
+    def dequantize(self, idx: torch.Tensor) -> torch.Tensor:
+        """Code lookup ``(..., ) int64 -> (..., d)`` (``vae.py:333``)."""
+        return self._p.dequantize(idx.unsqueeze(-1), first_stage=self._q)
+
+
+class _RVQFunction(torch.autograd.Function):
+    """Straight-through quantization + commit loss with hand-written backward.
+
+    forward:  xq (kernel), out = x + (xq - x)            [value of x + (xq - x).detach()]
+              commit = w * sum_q mean((r_q - sg z_q)^2) (+ sum_q mean((sg r_q - z_q)^2) for "base")
+    backward: d out / d x = I ; d commit / d x = w * 2/(N d) * sum_q r_{q+1} ;
+              d commit / d C_q[k] = -2/(N d) * sum_{n: idx=k} r_{q+1}[n]   ("base" only)
+    """
+
+    @staticmethod
+    def forward(ctx, x, codebooks, mod, nq, update):
+        xq, idx, commit_sq = mod._encode(x, nq, update)
+        N = idx.numel() // nq
+        w = mod.commitment_weight + (1.0 if mod.quantizer_class == "base" else 0.0)
+        commit = (commit_sq.sum() * (w / (N * mod.dim))).to(torch.float32)
+        ctx.mod, ctx.nq = mod, nq
+        ctx.save_for_backward(x, idx, codebooks)
+        ctx.mark_non_differentiable(idx)
+        out = x + (xq - x)
+        return out, idx, commit
+
+    @staticmethod
+    def backward(ctx, g_out, _g_idx, g_commit):
+        x, idx, codebooks = ctx.saved_tensors
+        mod, nq = ctx.mod, ctx.nq
+        d = mod.dim
+        gx = g_out if ctx.needs_input_grad[0] else None
+        gcb = None
+        need_cb = ctx.needs_input_grad[1] and mod.quantizer_class == "base"
+        if g_commit is not None and (ctx.needs_input_grad[0] or need_cb):
+            xf = x.reshape(-1, d)
+            flat = idx.reshape(-1, nq)
+            N = flat.shape[0]
+            coef = g_commit * (2.0 / (N * d))
+            r = xf
+            acc = torch.zeros_like(xf)
+            if need_cb:
+                gcb = torch.zeros_like(codebooks)
+            for q in range(nq):
+                r = r - codebooks[q].detach()[flat[:, q]]
+                acc = acc + r
+                if need_cb:
+                    gcb[q].index_add_(0, flat[:, q], r * (-coef))
+            if ctx.needs_input_grad[0]:
+                gxc = (acc * (coef * mod.commitment_weight)).reshape(x.shape)
+                gx = gxc if gx is None else gx + gxc
+        return gx, gcb, None, None, None
+
+
+class ResidualQuantizer(nn.Module):
+    """Residual vector quantizer on B200 (see module docstring for the interface it mirrors)."""
+
+    def __init__(self, num_quantizers, dim, quantizer_class="ema", codebook_sizes=1024,
+                 vq_cutoff_freq=1, use_som=True, som_kernel_type="hard",
+                 decay=EMA_DECAY, eps=EMA_EPS, commitment_weight=1.0, algo="tensor"):
+        super().__init__()
+        if quantizer_class not in ("ema", "base"):
+            raise ValueError(f"quantizer_class must be 'ema' or 'base', got {quantizer_class!r}")
+        self.num_quantizers = int(num_quantizers)
+        self.dim = int(dim)
+        self.quantizer_class = quantizer_class
+        self.codebook_sizes: List[int] = [int(k) for k in tuple_checker(codebook_sizes, self.num_quantizers)]
+        self.vq_cutoff_freq = float(vq_cutoff_freq)
+        self.use_som = bool(use_som)
+        self.som_kernel_type = som_kernel_type
+        self.decay, self.eps, self.commitment_weight = float(decay), float(eps), float(commitment_weight)
+        self.algo = algo
+        K = max(self.codebook_sizes)
+        self.K = K
+        cb = torch.randn(self.num_quantizers, K, self.dim)   # ASSUMED init
+        if quantizer_class == "base":
+            self.codebooks = nn.Parameter(cb)
+        else:
+            self.register_buffer("codebooks", cb)
+        self.register_buffer("ema_count", torch.ones(self.num_quantizers, K))
+        self.register_buffer("ema_sum", cb.detach().clone())
+        self.register_buffer("k_valid", torch.tensor(self.codebook_sizes, dtype=torch.int32))
+        self.quantizers = [_Stage(self, q) for q in range(self.num_quantizers)]
+        self._derived = None       # (key, cb_op, cb_norm, cb_meta)
+        self._ws = None
+        self._stats = None
+        self.last_stats = None     # flat [sum | cnt] of the most recent update (kept for inspection)
+
+    # ------------------------------------------------------------------ derived operands / scratch
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._derived = self._ws = self._stats = None
+        return out
+
+    def _check_device(self, t: torch.Tensor):
+        if not t.is_cuda:
+            raise RVQError("ResidualQuantizer runs on sm_100a only: got a CPU tensor (there is no CPU path)")
+        if self.codebooks.device != t.device:
+            raise RVQError(f"input on {t.device} but codebooks on {self.codebooks.device}")
+
+    def invalidate(self):
+        """Call after writing ``codebooks`` in place outside this class."""
+        self._derived = None
+
+    def _prepared(self):
+        cb = self.codebooks.detach()
+        key = (cb.data_ptr(), cb._version, str(cb.device))
+        if self._derived is None or self._derived[0] != key:
+            lib = _lib.load()
+            nq, K, d = self.num_quantizers, self.K, self.dim
+            ob, nb, mb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            _lib.check(lib.rvq_prepared_bytes(nq, K, d, C.byref(ob), C.byref(nb), C.byref(mb)), "rvq_prepared_bytes")
+            op = torch.empty(ob.value // 2, dtype=torch.float16, device=cb.device)
+            nrm = torch.empty(nb.value // 4, dtype=torch.float32, device=cb.device)
+            meta = torch.empty(mb.value // 4, dtype=torch.float32, device=cb.device)
+            with torch.cuda.device(cb.device):
+                _lib.check(lib.rvq_prepare_codebooks(_ptr(cb), _ptr(self.k_valid), nq, K, d, _ptr(op), _ptr(nrm),
+                                                     _ptr(meta), _stream()), "rvq_prepare_codebooks")
+            self._derived = (key, op, nrm, meta)
+        return self._derived[1:]
+
+    def _workspace(self, device):
+        if self._ws is None or self._ws.device != device:
+            lib = _lib.load()
+            n = C.c_size_t()
+            _lib.check(lib.rvq_workspace_bytes(self.num_quantizers, self.K, self.dim, 0, C.byref(n)),
+                       "rvq_workspace_bytes")
+            self._ws = torch.empty(n.value, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _stats_buffers(self, device):
+        nq, K, d = self.num_quantizers, self.K, self.dim
+        if self._stats is None or self._stats.device != device:
+            self._stats = torch.empty(nq * K * d + nq * K, dtype=torch.float32, device=device)
+        flat = self._stats
+        return flat, flat[: nq * K * d], flat[nq * K * d:]
+
+    # ------------------------------------------------------------------ the hot path
+    def _encode(self, x: torch.Tensor, nq: int, update: bool):
+        """Run K1(+K2) [+ all-reduce + K3] on ``x`` (..., L, d); returns (xq like x, idx (..., L, nq), commit_sq)."""
+        lib = _lib.load()
+        self._check_device(x)
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.detach()
+        x3, N, L, sb, sl, sd = _frame_addressing(x)
+        op, nrm, meta = self._prepared()
+        cb = self.codebooks.detach()
+        dev = x3.device
+        xq = torch.empty_strided(x3.shape, x3.stride(), dtype=torch.float32, device=dev)
+        idx = torch.empty((N, nq), dtype=torch.int64, device=dev)
+        commit_sq = torch.empty(nq, dtype=torch.float64, device=dev)
+        ws = self._workspace(dev)
+        ssum = scnt = flat = None
+        if update:
+            flat, ssum, scnt = self._stats_buffers(dev)
+            flat.zero_()
+        flags = RVQ_ALGO_EXACT_SCAN if self.algo == "exact_scan" else RVQ_ALGO_TENSOR
+        with torch.cuda.device(dev):
+            _lib.check(lib.rvq_encode(_ptr(x3), N, L, sb, sl, sd, self.dim, nq, self.K, _ptr(cb), _ptr(op), _ptr(nrm),
+                                      _ptr(meta), _ptr(xq), _ptr(idx), _ptr(commit_sq), _ptr(ssum), _ptr(scnt),
+                                      _ptr(ws), ws.numel(), flags, _stream()), "rvq_encode")
+            if update:
+                # the only place the path crosses frame shards: one SUM all-reduce of [sum | cnt]
+                if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                        and torch.distributed.get_world_size() > 1:
+                    torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+                _lib.check(lib.rvq_ema_finalize(_ptr(cb), _ptr(self.ema_count), _ptr(self.ema_sum), _ptr(ssum),
+                                                _ptr(scnt), _ptr(self.k_valid), nq, self.K, self.dim,
+                                                self.decay, self.eps, _stream()), "rvq_ema_finalize")
+                self._derived = None     # codebooks changed: operands are rebuilt before the next call
+                self.last_stats = flat
+        xq = xq.reshape(x.shape) if xq.shape != x.shape else xq
+        return xq, idx.reshape(*x.shape[:-1], nq), commit_sq
+
+    def forward(self, x, n=None, update_codebook=False, prioritize_early=False):
+        if prioritize_early:
+            raise NotImplementedError("prioritize_early=True: semantics unknown (never used by the reference)")
+        nq = self.num_quantizers if n is None else int(n)
+        if not 1 <= nq <= self.num_quantizers:
+            raise ValueError(f"n must be in [1, {self.num_quantizers}], got {nq}")
+        if x.shape[-1] != self.dim:
+            raise ValueError(f"last dimension must be {self.dim}, got {tuple(x.shape)}")
+        update = bool(update_codebook) and self.training and self.quantizer_class == "ema"
+        if torch.is_grad_enabled() and (x.requires_grad or (self.quantizer_class == "base" and
+                                                            self.codebooks.requires_grad)):
+            out, idx, commit = _RVQFunction.apply(x, self.codebooks, self, nq, update)
+            return out, idx, commit
+        xq, idx, commit_sq = self._encode(x, nq, update)
+        N = idx.numel() // nq
+        w = self.commitment_weight + (1.0 if self.quantizer_class == "base" else 0.0)
+        commit = (commit_sq.sum() * (w / (N * self.dim))).to(torch.float32)
+        return xq, idx, commit
+
+    # ------------------------------------------------------------------ decode side
+    def dequantize(self, idx: torch.Tensor, first_stage: int = 0) -> torch.Tensor:
+        """Sum of code vectors: idx (..., n) int64 -> (..., d) using stages first_stage .. first_stage+n-1."""
+        lib = _lib.load()
+        self._check_device(idx)
+        nq = idx.shape[-1]
+        flat = idx.reshape(-1, nq).contiguous().long()
+        N = flat.shape[0]
+        out = torch.empty((N, self.dim), dtype=torch.float32, device=idx.device)
+        if N:
+            cb = self.codebooks.detach()
+            with torch.cuda.device(idx.device):
+                _lib.check(lib.rvq_dequantize(_ptr(cb), _ptr(flat), N, N, 0, self.dim, 1, self.dim, first_stage, nq,
+                                              self.K, None, 0, _ptr(out), _stream()), "rvq_dequantize")
+        return out.reshape(*idx.shape[:-1], self.dim)
+
+    # ------------------------------------------------------------------ epoch-level API
+    def get_stale_clusters(self):
+        """Per stage, the number of codes whose EMA usage share is below ``vq_cutoff_freq / K``."""
+        cnt = self.ema_count
+        out = []
+        for q in range(self.num_quantizers):
+            K = self.codebook_sizes[q]
+            c = cnt[q, :K]
+            freq = c / c.sum().clamp_min(1e-30)
+            out.append(int((freq < self.vq_cutoff_freq / K).sum()))
+        return out
+
+    def update_cutoff(self, new_cutoff=None, ratio=None):
+        if new_cutoff is not None:
+            self.vq_cutoff_freq = float(new_cutoff)
+        if ratio is not None:
+            self.vq_cutoff_freq *= float(ratio)
+
+    def extra_repr(self):
+        return (f"num_quantizers={self.num_quantizers}, dim={self.dim}, K={self.codebook_sizes}, "
+                f"class={self.quantizer_class!r}, algo={self.algo!r}")

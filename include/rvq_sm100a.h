@@ -1,0 +1,115 @@
+/*
+ * rvq_sm100a.h -- C ABI of librvq_sm100a.so: the B200 (sm_100a) residual-vector-quantization
+ * hot path that replaces the body of `som_quantizer.ResidualQuantizer.forward`
+ * (third-party quantization-maps package imported at /root/reference/networks/vae.py:6 and
+ * called at /root/reference/networks/vae.py:315-318).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked HOST;
+ *   - every entry enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising the host (except where noted);
+ *   - returns 0 on success, a negative rvq_status on failure; the message of the last failure
+ *     on the calling thread is returned by rvq_last_error(); nothing throws across the ABI;
+ *   - there is no CPU path: a device that is not compute capability 10.x is refused
+ *     (RVQ_ERR_ARCH).
+ *
+ * Shapes: nq stages, K codes per stage, d features, N frames.  Kpad = K rounded up to 256.
+ */
+#ifndef RVQ_SM100A_H
+#define RVQ_SM100A_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVQ_ABI_VERSION 3
+
+typedef enum {
+    RVQ_OK = 0,
+    RVQ_ERR_ARG = -1,      /* bad shape / null pointer / unsupported size            */
+    RVQ_ERR_ARCH = -2,     /* current device is not sm_100                           */
+    RVQ_ERR_CUDA = -3,     /* CUDA runtime / driver error (launch, attribute, ...)   */
+    RVQ_ERR_WORKSPACE = -4 /* workspace too small                                    */
+} rvq_status;
+
+/* encode flags */
+#define RVQ_ALGO_TENSOR 0      /* tcgen05 fp16 filter + exact fp32 re-rank (product path)       */
+#define RVQ_ALGO_EXACT_SCAN 1  /* exact fp32 CUDA-core scan of every code (verification, tiny N) */
+#define RVQ_FLAG_ALGO_MASK 0xF
+
+int rvq_version(void);
+const char* rvq_last_error(void);
+/* 1 if `device` (ordinal) can run the kernels (compute capability 10.x), 0 if not, <0 on error. HOST. */
+int rvq_device_supported(int device);
+
+/* Sizes (HOST pointers out) of the derived codebook operands written by rvq_prepare_codebooks:
+ *   op_bytes   : fp16 [nq, Kpad, d]  = -2 * 2^b_q * C_q            (UMMA B operand, K-major rows)
+ *   norm_bytes : fp32 [nq, Kpad]     = 2^(2 b_q) * ||c||^2, padding codes = 2^100
+ *   meta_bytes : fp32 [nq, 8]        = {2^b_q, max_k ||c_k||_2, max |c|, K_valid, 0...}       */
+int rvq_prepared_bytes(int nq, int K, int d, size_t* op_bytes, size_t* norm_bytes, size_t* meta_bytes);
+
+/* K0. Derive the tensor-core operands from the fp32 master codebooks cb[nq, K, d].
+ * k_valid (DEVICE int[nq], nullable): number of real codes per stage (<= K); codes beyond it
+ * can never be selected.  Must be re-run after every codebook change
+ * (replaces nothing in the reference: the reference uses the fp32 codebook directly). */
+int rvq_prepare_codebooks(const float* cb, const int* k_valid, int nq, int K, int d,
+                          void* cb_op, float* cb_norm, float* cb_meta, void* stream);
+
+/* Scratch needed by rvq_encode for N frames. HOST pointer out. */
+int rvq_workspace_bytes(int nq, int K, int d, long long N, size_t* out);
+
+/* K1 (+K2 fused). Replaces the per-stage loop of ResidualQuantizer.forward
+ * (distance -> argmin -> gather -> residual subtract -> [EMA statistics]) called at
+ * /root/reference/networks/vae.py:315-318.
+ *
+ *   x        fp32, N = (N / L) * L frames addressed as x[(n / L) * stride_b + (n % L) * stride_l + i * stride_d]
+ *            (the reference passes a (B, L, d) VIEW of a (B, d, L) tensor: stride_l = 1, stride_d = L;
+ *            contiguous (N, d): L = N, stride_b = 0, stride_l = d, stride_d = 1)
+ *   cb       fp32 master codebooks [nq_total, K, d]; stages 0..nq_use-1 are used
+ *   cb_op / cb_norm / cb_meta   outputs of rvq_prepare_codebooks for the same cb
+ *   xq       fp32 out, same addressing as x: sum of the selected code vectors (= x - final residual)
+ *   idx      int64 out [N, nq_use] (what torch.nn.functional.one_hot needs, utils.py:253)
+ *   commit_sq  fp64 out [nq_use]: sum over frames and features of (r_q - z_q)^2 per stage
+ *              (commit loss of stage q = commit_sq[q] / (N*d)); zeroed by the call
+ *   stats_sum  fp32 [nq_total, K, d] nullable, stats_cnt fp32 [nq_total, K] nullable: EMA statistics,
+ *              ACCUMULATED into (caller zeroes): cnt[q,k] += #{n: idx=k}, sum[q,k,:] += r_q[n,:]
+ *   ws / ws_bytes   scratch of at least rvq_workspace_bytes
+ *   flags    RVQ_ALGO_*                                                                          */
+int rvq_encode(const float* x, long long N, long long L, long long stride_b, long long stride_l,
+               long long stride_d, int d, int nq_use, int K,
+               const float* cb, const void* cb_op, const float* cb_norm, const float* cb_meta,
+               float* xq, long long* idx, double* commit_sq,
+               float* stats_sum, float* stats_cnt,
+               void* ws, size_t ws_bytes, int flags, void* stream);
+
+/* K3. EMA refresh of one call's statistics (after the cross-GPU all-reduce of stats_*):
+ *   ema_count = decay*ema_count + (1-decay)*cnt;  ema_sum = decay*ema_sum + (1-decay)*sum;
+ *   cb[k] = ema_sum[k] / ((ema_count[k]+eps)/(n+K_valid*eps)*n),  n = sum_k ema_count[k]
+ * over stages 0..nq_use-1.  k_valid as in rvq_prepare_codebooks. */
+int rvq_ema_finalize(float* cb, float* ema_count, float* ema_sum,
+                     const float* stats_sum, const float* stats_cnt, const int* k_valid,
+                     int nq_use, int K, int d, float decay, float eps, void* stream);
+
+/* Code lookup (ResidualQuantizer.quantizers[i].dequantize, /root/reference/networks/vae.py:333,
+ * summed over stages as CausalVQAE.sample does at vae.py:329-334):
+ *   out[n,:] (+)= sum_q w[q] * cb[q0+q, idx[n,q], :]   (w nullable = all ones; HOST float[nq_use])
+ * out addressed like x in rvq_encode.  accumulate != 0 adds into out. */
+int rvq_dequantize(const float* cb, const long long* idx, long long N, long long L,
+                   long long stride_b, long long stride_l, long long stride_d,
+                   int d, int q0, int nq_use, int K, const float* w, int accumulate,
+                   float* out, void* stream);
+
+/* Bring-up / test hook: run ONE stage of the tensor-core filter for the first 128 frames of x
+ * (contiguous [128, d]) and write the approximate scaled scores fp32 [128, Kpad] and the per-row
+ * scale 2^a [128].  Not used by the product path. */
+int rvq_debug_stage_scores(const float* x, int d, int K, int stage,
+                           const void* cb_op, const float* cb_norm, const float* cb_meta,
+                           float* scores, float* row_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVQ_SM100A_H */

@@ -1,0 +1,271 @@
+"""CPU restatement of the reference's RVQ bottleneck -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+PARITY UNPINNED.  The arithmetic of this path is not in the reference tree: the
+reference imports it from the third-party package ``som_quantizer``
+(LumenPallidium/quantization-maps; ``/root/reference/networks/vae.py:6``), which
+is not vendored, not version-pinned (``/root/reference/environment.yml`` does not
+list it) and not installable here (no network).  The reference ships no tests and
+no golden vectors.  This file therefore restates
+
+* the boundary contract that the reference's own call sites pin
+  (``vae.py:245-251`` ctor kwargs, ``vae.py:315-318`` call and return order,
+  ``vae.py:333`` ``quantizers[i].dequantize``, ``vae.py:350-351`` ``update_cutoff``,
+  ``training.py:183,435,454,461`` attributes, ``utils.py:239-257`` index dtype/shape,
+  ``utils.py:212-220`` ``tuple_checker``), and
+* the published algorithm named by BASELINE.json's north star (distance to all
+  codes -> argmin -> gather -> residual subtract -> EMA count/sum), with the EMA
+  constants of the lineage the reference credits (``README.md:26-27``: Jukebox /
+  rosinality VQ-VAE: decay 0.99, Laplace smoothing eps 1e-5).
+
+Every choice not pinned by a call site is marked ASSUMED.
+Independent cross-check: ``tests/test_oracle.py`` compares the index chain with
+HuggingFace ``EncodecResidualVectorQuantizer.encode`` (an unrelated implementation
+of the same distance -> argmax(-dist) -> residual chain).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py`` (cpu_baseline /
+``--impl reference``) may import this module.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+EMA_DECAY = 0.99      # ASSUMED (rosinality / Jukebox)
+EMA_EPS = 1e-5        # ASSUMED (rosinality Laplace smoothing)
+
+
+def tuple_checker(item, length):
+    """Restates ``/root/reference/networks/utils.py:212-220``: scalar -> list of
+    ``length`` copies; tuple/list is length-checked and returned unchanged."""
+    if isinstance(item, (int, float, str)):
+        item = [item] * length
+    elif isinstance(item, (tuple, list)):
+        assert len(item) == length, f"Expected tuple of length {length}, got {len(item)}"
+    return item
+
+
+def approximate_square_root(n: int) -> Tuple[int, int]:
+    """(h, w) with h*w == n and h the largest divisor <= sqrt(n) (SOM grid shape,
+    ``utils.py:244-245,257`` needs height*width == K)."""
+    h = int(math.isqrt(n))
+    while h > 1 and n % h:
+        h -= 1
+    return h, n // h
+
+
+# --------------------------------------------------------------------------
+# functional core (the arithmetic the CUDA path is checked against)
+# --------------------------------------------------------------------------
+def stage_scores(r: torch.Tensor, cb: torch.Tensor) -> torch.Tensor:
+    """score[n,k] = ||c_k||^2 - 2 r_n.c_k  (fp32; ||r||^2 dropped, argmin-invariant).
+    ASSUMED form."""
+    return (cb * cb).sum(1)[None, :] - 2.0 * (r @ cb.t())
+
+
+def rvq_encode_ref(x2d: torch.Tensor, codebooks: Sequence[torch.Tensor], nq_use: Optional[int] = None,
+                   chunk: int = 65536):
+    """Encode ``x2d`` (N, d) fp32 through the first ``nq_use`` stages.
+
+    Returns ``(idx int64 (N, nq_use), xq fp32 (N, d), resid fp32 (N, d),
+    commit fp64-accumulated python floats per stage [nq_use])``.
+    Frames are processed in chunks so the N x K score matrix stays bounded.
+    """
+    nq = len(codebooks) if nq_use is None else int(nq_use)
+    x2d = x2d.float()
+    N, d = x2d.shape
+    idx = torch.empty(N, nq, dtype=torch.int64)
+    xq = torch.empty_like(x2d)
+    resid = torch.empty_like(x2d)
+    sq = [0.0] * nq
+    for s in range(0, N, chunk):
+        r = x2d[s:s + chunk].clone()
+        acc = torch.zeros_like(r)
+        for q in range(nq):
+            cb = codebooks[q].float()
+            i = stage_scores(r, cb).argmin(dim=1)      # lowest index wins exact ties (torch CPU)
+            z = cb[i]
+            r = r - z
+            acc = acc + z
+            sq[q] += float((r.double() ** 2).sum())
+            idx[s:s + chunk, q] = i
+        xq[s:s + chunk] = acc
+        resid[s:s + chunk] = r
+    commit = [v / (N * d) for v in sq]
+    return idx, xq, resid, commit
+
+
+def ema_stats_ref(r_in: torch.Tensor, idx_q: torch.Tensor, K: int):
+    """Per-stage statistics: count[k] = #{n: idx=k}; sum[k] = sum of stage-input residuals."""
+    cnt = torch.bincount(idx_q, minlength=K).float()
+    sm = torch.zeros(K, r_in.shape[1], dtype=torch.float32).index_add_(0, idx_q, r_in.float())
+    return cnt, sm
+
+
+def ema_finalize_ref(cb, ema_count, ema_sum, cnt, sm, decay=EMA_DECAY, eps=EMA_EPS):
+    """EMA + Laplace-smoothed codebook refresh (ASSUMED constants; rosinality form)."""
+    K = cb.shape[0]
+    ema_count = decay * ema_count + (1.0 - decay) * cnt
+    ema_sum = decay * ema_sum + (1.0 - decay) * sm
+    n_tot = ema_count.sum()
+    smoothed = (ema_count + eps) / (n_tot + K * eps) * n_tot
+    cb = ema_sum / smoothed[:, None]
+    return cb, ema_count, ema_sum
+
+
+def stage_residuals_from_indices(x2d: torch.Tensor, codebooks, idx: torch.Tensor) -> List[torch.Tensor]:
+    """Residual entering each stage when the chain follows ``idx`` (teacher forcing)."""
+    r = x2d.float().clone()
+    out = []
+    for q in range(idx.shape[1]):
+        out.append(r)
+        r = r - codebooks[q].float()[idx[:, q]]
+    out.append(r)
+    return out
+
+
+def adjudicate_indices(x2d, codebooks, idx_test: torch.Tensor, eps_scale: float = 8.0, chunk: int = 32768):
+    """Teacher-forced index parity check used by the GPU tests.
+
+    For every stage the oracle argmin is recomputed on the residual obtained by
+    following ``idx_test``'s own prefix.  A disagreement is *legitimate* only when
+    the two candidate scores differ, in fp64, by at most
+    ``eps_tie = eps_scale * d * 2**-24 * (||r||*||c||_max + ||c||_max^2)`` (fp32 dot-product
+    reordering noise).  Returns ``dict(n_mismatch, n_illegal, max_gap_ratio)``.
+    """
+    x2d = x2d.float()
+    N, d = x2d.shape
+    nq = idx_test.shape[1]
+    n_mis = 0
+    n_bad = 0
+    worst = 0.0
+    for s in range(0, N, chunk):
+        r = x2d[s:s + chunk].clone()
+        it = idx_test[s:s + chunk]
+        for q in range(nq):
+            cb = codebooks[q].float()
+            io = stage_scores(r, cb).argmin(dim=1)
+            dif = (io != it[:, q]).nonzero().flatten()
+            if dif.numel():
+                n_mis += int(dif.numel())
+                rr = r[dif].double()
+                ca = cb[io[dif]].double()
+                cbk = cb[it[dif, q]].double()
+                sa = (ca * ca).sum(1) - 2.0 * (rr * ca).sum(1)
+                sb = (cbk * cbk).sum(1) - 2.0 * (rr * cbk).sum(1)
+                cmax = cb.double().norm(dim=1).max()
+                eps_tie = eps_scale * d * 2.0 ** -24 * (rr.norm(dim=1) * cmax + cmax * cmax)
+                ratio = ((sb - sa).abs() / eps_tie)
+                worst = max(worst, float(ratio.max()))
+                n_bad += int((ratio > 1.0).sum())
+            r = r - cb[it[:, q]]
+    return dict(n_mismatch=n_mis, n_illegal=n_bad, max_gap_ratio=worst)
+
+
+# --------------------------------------------------------------------------
+# nn.Module with the reference's call-site contract
+# --------------------------------------------------------------------------
+class _SOMGrid:
+    def __init__(self, K):
+        self.height, self.width = approximate_square_root(K)
+
+
+class _StageRef:
+    """``quantizers[i]`` view: ``.dequantize`` (``vae.py:333``), ``.som`` (``utils.py:244-245``)."""
+
+    def __init__(self, parent, q):
+        self._p, self._q = parent, q
+        if parent.use_som:
+            self.som = _SOMGrid(parent.codebook_sizes[q])
+
+    @property
+    def codebook(self):
+        return self._p.codebooks[self._q][: self._p.codebook_sizes[self._q]]
+
+    def dequantize(self, idx):
+        return self.codebook[idx]
+
+
+class ResidualQuantizerRef(nn.Module):
+    """Oracle ``ResidualQuantizer`` (ctor kwargs: ``vae.py:245-251``; call: ``vae.py:315-318``)."""
+
+    def __init__(self, num_quantizers, dim, quantizer_class="ema", codebook_sizes=1024,
+                 vq_cutoff_freq=1, use_som=True, som_kernel_type="hard",
+                 decay=EMA_DECAY, eps=EMA_EPS, commitment_weight=1.0):
+        super().__init__()
+        self.num_quantizers = int(num_quantizers)
+        self.dim = int(dim)
+        self.quantizer_class = quantizer_class
+        self.codebook_sizes = [int(k) for k in tuple_checker(codebook_sizes, self.num_quantizers)]
+        self.vq_cutoff_freq = float(vq_cutoff_freq)
+        self.use_som = bool(use_som)
+        self.som_kernel_type = som_kernel_type
+        self.decay, self.eps, self.commitment_weight = float(decay), float(eps), float(commitment_weight)
+        Kmax = max(self.codebook_sizes)
+        cb = torch.randn(self.num_quantizers, Kmax, self.dim)          # ASSUMED init
+        if quantizer_class == "base":
+            self.codebooks = nn.Parameter(cb)
+        else:
+            self.register_buffer("codebooks", cb)
+        self.register_buffer("ema_count", torch.ones(self.num_quantizers, Kmax))
+        self.register_buffer("ema_sum", cb.detach().clone())
+        self.quantizers = [_StageRef(self, q) for q in range(self.num_quantizers)]
+
+    def forward(self, x, n=None, update_codebook=False, prioritize_early=False):
+        if prioritize_early:
+            raise NotImplementedError("prioritize_early=True: semantics unknown (never used by the reference)")
+        nq = self.num_quantizers if n is None else int(n)
+        shp = x.shape
+        r = x.reshape(-1, self.dim).float()
+        N = r.shape[0]
+        xq = torch.zeros_like(r)
+        commit = r.new_zeros(())
+        idxs = []
+        for q in range(nq):
+            K = self.codebook_sizes[q]
+            cb = self.codebooks[q, :K]
+            with torch.no_grad():
+                i = stage_scores(r.detach(), cb.detach()).argmin(dim=1)
+            z = cb[i]
+            commit = commit + self.commitment_weight * ((r - z.detach()) ** 2).mean()
+            if self.quantizer_class == "base":
+                commit = commit + ((r.detach() - z) ** 2).mean()       # codebook loss (VQ-VAE), ASSUMED
+            if update_codebook and self.training and self.quantizer_class == "ema":
+                with torch.no_grad():
+                    cnt, sm = ema_stats_ref(r.detach(), i, K)
+                    if torch.distributed.is_available() and torch.distributed.is_initialized():
+                        torch.distributed.all_reduce(cnt)
+                        torch.distributed.all_reduce(sm)
+                    ncb, nc, ns = ema_finalize_ref(cb, self.ema_count[q, :K], self.ema_sum[q, :K], cnt, sm,
+                                                   self.decay, self.eps)
+                    self._pending = getattr(self, "_pending", [])
+                    self._pending.append((q, K, ncb, nc, ns))
+            xq = xq + z.detach()
+            r = r - z.detach()
+            idxs.append(i)
+        for (q, K, ncb, nc, ns) in getattr(self, "_pending", []):       # takes effect from the NEXT call
+            self.codebooks.data[q, :K] = ncb
+            self.ema_count[q, :K] = nc
+            self.ema_sum[q, :K] = ns
+        self._pending = []
+        xf = x.reshape(-1, self.dim)
+        x_quantized = (xf + (xq - xf).detach()).reshape(shp)           # straight-through
+        index = torch.stack(idxs, dim=-1).reshape(*shp[:-1], nq)
+        return x_quantized, index, commit
+
+    def get_stale_clusters(self):
+        out = []
+        for q in range(self.num_quantizers):
+            K = self.codebook_sizes[q]
+            c = self.ema_count[q, :K]
+            freq = c / c.sum().clamp_min(1e-30)
+            out.append(int((freq < self.vq_cutoff_freq / K).sum()))
+        return out
+
+    def update_cutoff(self, new_cutoff=None, ratio=None):
+        if new_cutoff is not None:
+            self.vq_cutoff_freq = float(new_cutoff)
+        if ratio is not None:
+            self.vq_cutoff_freq *= float(ratio)
