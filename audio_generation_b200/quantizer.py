@@ -226,7 +226,7 @@ class ResidualQuantizer(nn.Module):
         return flat, flat[: nq * K * d], flat[nq * K * d:]
 
     # ------------------------------------------------------------------ the hot path
-    def _encode(self, x: torch.Tensor, nq: int, update: bool):
+    def _encode(self, x: torch.Tensor, nq: int, update: bool, ws: Optional[torch.Tensor] = None):
         """Run K1(+K2) [+ all-reduce + K3] on ``x`` (..., L, d); returns (xq like x, idx (..., L, nq), commit_sq)."""
         lib = _lib.load()
         self._check_device(x)
@@ -240,7 +240,8 @@ class ResidualQuantizer(nn.Module):
         xq = torch.empty_strided(x3.shape, x3.stride(), dtype=torch.float32, device=dev)
         idx = torch.empty((N, nq), dtype=torch.int64, device=dev)
         commit_sq = torch.empty(nq, dtype=torch.float64, device=dev)
-        ws = self._workspace(dev)
+        if ws is None:
+            ws = self._workspace(dev)
         ssum = scnt = flat = None
         if update:
             flat, ssum, scnt = self._stats_buffers(dev)
@@ -319,3 +320,53 @@ class ResidualQuantizer(nn.Module):
     def extra_repr(self):
         return (f"num_quantizers={self.num_quantizers}, dim={self.dim}, K={self.codebook_sizes}, "
                 f"class={self.quantizer_class!r}, algo={self.algo!r}")
+
+
+class HostEncoder:
+    """End-to-end encode of HOST-resident frames: pinned host -> device -> RVQ -> codes back to pinned host.
+
+    Frames are cut into chunks that ride two CUDA streams so that the host->device copy of chunk i+1 and the
+    device->host copy of chunk i-1 overlap the kernel of chunk i.  This is the call a serving user makes
+    when latents arrive from another process; ``bench.py`` times it as the ``e2e`` figure.
+    """
+
+    def __init__(self, quantizer: ResidualQuantizer, chunk_frames: int = 1 << 17, n_buffers: int = 3):
+        self.q = quantizer
+        self.chunk = int(chunk_frames)
+        self.nbuf = int(n_buffers)
+        self._streams = None
+        self._bufs = None
+
+    def _setup(self, dev, nq):
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.nbuf)]
+            d = self.q.dim
+            self._bufs = [torch.empty(self.chunk, d, dtype=torch.float32, device=dev) for _ in range(self.nbuf)]
+            self._wss = [torch.empty_like(self.q._workspace(dev)) for _ in range(self.nbuf)]
+
+    @torch.no_grad()
+    def encode(self, x_host: torch.Tensor, idx_host: Optional[torch.Tensor] = None, n: Optional[int] = None):
+        """x_host: pinned (N, d) fp32 on the CPU; returns pinned int64 (N, nq) codes (host)."""
+        q = self.q
+        nq = q.num_quantizers if n is None else int(n)
+        dev = q.codebooks.device
+        N = x_host.shape[0]
+        if idx_host is None:
+            idx_host = torch.empty((N, nq), dtype=torch.int64).pin_memory()
+        self._setup(dev, nq)
+        q._prepared()                      # operands built on the current stream before the side streams start
+        cur = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        for i, s0 in enumerate(range(0, N, self.chunk)):
+            st = self._streams[i % self.nbuf]
+            buf = self._bufs[i % self.nbuf]
+            m = min(self.chunk, N - s0)
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                buf[:m].copy_(x_host[s0:s0 + m], non_blocking=True)
+                _, idx, _ = q._encode(buf[:m], nq, False, ws=self._wss[i % self.nbuf])
+                idx_host[s0:s0 + m].copy_(idx, non_blocking=True)
+        for st in self._streams:
+            cur.wait_stream(st)
+        return idx_host
