@@ -6,7 +6,9 @@
 //
 // An 8-lane group owns one (row, code) pair.  Lane j of the group owns the float4 pieces
 // j, j+8, j+16, ... of the d-vector, accumulates dot and norm with fmaf in that order and
-// the 8 partials are combined by an xor-butterfly (1, 2, 4).
+// the 8 partials are combined by an xor-butterfly (1, 2, 4).  The batched variant scores NC codes
+// against one row with all loads of a 128-feature segment issued before the arithmetic (memory-level
+// parallelism); per code the operation order is identical, so results are bit-identical.
 #pragma once
 #include "ptx.cuh"
 
@@ -21,46 +23,86 @@ __device__ __forceinline__ bool better(float s, int k, float bs, int bk) {
     return (s < bs) || (s == bs && k < bk);  // lowest index wins exact ties (torch argmin on CPU)
 }
 
-// r: row vector (generic pointer: shared or global), c: code vector (global). d % 32 == 0.
-// All 8 lanes of the group return the same value.
-__device__ __forceinline__ float exact_score8(const float* __restrict__ r, const float* __restrict__ c, int d,
-                                              int sub) {
-    float dot = 0.f, nrm = 0.f;
-    for (int p = sub * 4; p < d; p += 32) {
-        const float4 rv = *reinterpret_cast<const float4*>(r + p);
-        const float4 cv = ldg_nc_v4(c + p);
-        dot = fmaf(rv.x, cv.x, dot);
-        dot = fmaf(rv.y, cv.y, dot);
-        dot = fmaf(rv.z, cv.z, dot);
-        dot = fmaf(rv.w, cv.w, dot);
-        nrm = fmaf(cv.x, cv.x, nrm);
-        nrm = fmaf(cv.y, cv.y, nrm);
-        nrm = fmaf(cv.z, cv.z, nrm);
-        nrm = fmaf(cv.w, cv.w, nrm);
+// r: row vector (generic pointer: shared or global), c[j]: code vectors (global). d % 32 == 0.
+// All 8 lanes of the group obtain the same out[j].
+template <int NC>
+__device__ __forceinline__ void exact_score8_n(const float* __restrict__ r, const float* const* c, int d, int sub,
+                                               float* out) {
+    float dot[NC], nrm[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) dot[j] = nrm[j] = 0.f;
+    for (int p0 = sub * 4; p0 < d; p0 += 128) {
+        float4 rv[4], cv[NC][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = p0 + i * 32;
+            if (p < d) {
+                rv[i] = *reinterpret_cast<const float4*>(r + p);
+#pragma unroll
+                for (int j = 0; j < NC; ++j) cv[j][i] = ldg_nc_v4(c[j] + p);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = p0 + i * 32;
+            if (p < d) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    dot[j] = fmaf(rv[i].x, cv[j][i].x, dot[j]);
+                    dot[j] = fmaf(rv[i].y, cv[j][i].y, dot[j]);
+                    dot[j] = fmaf(rv[i].z, cv[j][i].z, dot[j]);
+                    dot[j] = fmaf(rv[i].w, cv[j][i].w, dot[j]);
+                    nrm[j] = fmaf(cv[j][i].x, cv[j][i].x, nrm[j]);
+                    nrm[j] = fmaf(cv[j][i].y, cv[j][i].y, nrm[j]);
+                    nrm[j] = fmaf(cv[j][i].z, cv[j][i].z, nrm[j]);
+                    nrm[j] = fmaf(cv[j][i].w, cv[j][i].w, nrm[j]);
+                }
+            }
+        }
     }
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+    for (int j = 0; j < NC; ++j) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
+            nrm[j] += __shfl_xor_sync(0xffffffffu, nrm[j], o);
+        }
+        out[j] = fmaf(-2.f, dot[j], nrm[j]);
     }
-    return fmaf(-2.f, dot, nrm);
 }
 
-// Exact argmin over codes [k0, k1) for one row by ONE WARP (4 groups of 8 lanes, one code each per step).
-// Every lane returns the warp-wide best.
+__device__ __forceinline__ float exact_score8(const float* __restrict__ r, const float* __restrict__ c, int d,
+                                              int sub) {
+    const float* const cc[1] = {c};
+    float o[1];
+    exact_score8_n<1>(r, cc, d, sub, o);
+    return o[0];
+}
+
+// Exact argmin over codes [k0, k1) for one row by ONE WARP: 4 groups of 8 lanes, 2 codes per group per step
+// (8 codes per warp step).  Every lane returns the warp-wide best.
 __device__ __forceinline__ ScoreIdx exact_scan_warp(const float* __restrict__ r, const float* __restrict__ cbq,
                                                     int d, int k0, int k1, int lane) {
     const int sub = lane & 7, grp = lane >> 3;
     float bs = __int_as_float(0x7f800000);
     int bk = 0x7fffffff;
-    for (int kb = k0; kb < k1; kb += 4) {
-        const int k = kb + grp;
-        const bool valid = k < k1;
-        const float s = exact_score8(r, cbq + (size_t)(valid ? k : k0) * d, d, sub);
-        if (valid && better(s, k, bs, bk)) {
-            bs = s;
-            bk = k;
+    constexpr int NC = 2;
+    for (int kb = k0; kb < k1; kb += 4 * NC) {
+        int k[NC];
+        const float* cc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            k[j] = kb + j * 4 + grp;
+            cc[j] = cbq + (size_t)(k[j] < k1 ? k[j] : k0) * d;
         }
+        float s[NC];
+        exact_score8_n<NC>(r, cc, d, sub, s);
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+            if (k[j] < k1 && better(s[j], k[j], bs, bk)) {
+                bs = s[j];
+                bk = k[j];
+            }
     }
 #pragma unroll
     for (int o = 8; o < 32; o <<= 1) {

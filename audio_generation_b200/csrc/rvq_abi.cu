@@ -70,7 +70,12 @@ extern "C" int rvq_encode(const float* x, long long N, long long L, long long st
                           const float* cb_norm, const float* cb_meta, float* xq, long long* idx, double* commit_sq,
                           float* stats_sum, float* stats_cnt, void* ws, size_t ws_bytes, int flags, void* stream) {
     if (int e = rvq_check_shape("rvq_encode", nq_use, K, d)) return e;
-    if (N < 0 || L <= 0 || (N % L) != 0 && L < N) {
+    if (N == 0) {
+        if (!commit_sq) return RVQ_OK;
+        RVQ_CUDA(cudaMemsetAsync(commit_sq, 0, sizeof(double) * nq_use, static_cast<cudaStream_t>(stream)));
+        return RVQ_OK;
+    }
+    if (N < 0 || L <= 0 || (N % L) != 0) {
         set_error("rvq_encode: bad frame addressing N=%lld L=%lld", N, L);
         return RVQ_ERR_ARG;
     }

@@ -18,6 +18,7 @@
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 / 8-11 = epilogue groups 0 / 1 (accumulator buffers 0 / 1).
 #include <cuda.h>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -25,14 +26,17 @@
 
 namespace rvq {
 
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_THREADS = 256;
-constexpr int EPI_WARP0 = 4;
+constexpr int SCAN_WARP0 = 4;
+constexpr int SCAN_THREADS = 256;
+constexpr int UPD_WARP0 = 12;
+constexpr int UPD_THREADS = 128;
+constexpr int NUM_THREADS = UPD_WARP0 * 32 + UPD_THREADS;  // 512
 constexpr int MAX_STAGES_RING = 6;
 constexpr int MAX_NQ = 64;
 constexpr uint32_t A_SLICE_BYTES = TILE_M * KSLICE * 2;   // 16 KiB
 constexpr uint32_t B_STAGE_BYTES = CHUNK_N * KSLICE * 2;  // 32 KiB
-constexpr uint32_t BAR_EPI = 1;                           // named barrier id for the 256 epilogue threads
+constexpr uint32_t BAR_SCAN = 1;  // named barrier of the 256 scan threads
+constexpr uint32_t BAR_UPD = 2;   // named barrier of the update threads
 constexpr float BIG = 3.0e38f;
 
 struct RowAddrT {
@@ -54,21 +58,22 @@ struct EncParams {
     float* stats_sum;
     float* stats_cnt;
     float* r_scratch;  // per-CTA [128, d] fp32 when the residual tile does not fit in shared memory
-    int num_tiles, nstage, r_in_smem, r_pitch;
-    uint32_t off_B, off_R, off_misc;  // A tile at offset 0
+    int num_tiles, nstage, nslots, r_pitch;
+    uint32_t off_B, off_misc;  // A tiles (one per slot) at offset 0
     float* dbg_scores;                // [128, Kpad] (bring-up hook) or null
     float* dbg_rowscale;              // [128] or null
+    unsigned long long* prof;         // [8] cycle / event counters (RVQ_PROFILE=1) or null
 };
 
 struct __align__(16) Misc {
-    uint64_t full[MAX_STAGES_RING], empty[MAX_STAGES_RING], tmem_full[2], tmem_empty[2], a_ready;
+    uint64_t full[MAX_STAGES_RING], empty[MAX_STAGES_RING], tmem_full[2], tmem_empty[2], a_ready[2], scan_done[2];
     uint32_t tmem_base;
-    int dirty_count;
-    float row_na[TILE_M], row_delta[TILE_M];
-    int cand1[TILE_M], cand2[TILE_M], ncand[TILE_M];
+    int dirty_count[2];
+    float row_na[2][TILE_M], row_delta[2][TILE_M];      // per tile slot
+    int cand1[2][TILE_M], cand2[2][TILE_M], ncand[2][TILE_M];
+    int dirty_rows[2][TILE_M];
     float mrg_v[3][TILE_M];
     int mrg_k[2][TILE_M];
-    int dirty_rows[TILE_M];
     float dirty_s[8];
     int dirty_k[8];
     double commit_acc[MAX_NQ];
@@ -94,7 +99,8 @@ __device__ __forceinline__ uint32_t a_tile_offset(int row, int col) {
 // All 32 lanes of the warp must call this together (8-lane shuffles with a full mask); `active` gates effects.
 //   kwin < 0      : stage-0 initialisation (no subtraction)
 //   next_stage<0  : last stage (no operand for a next stage)
-__device__ __forceinline__ void finish_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int row,
+__device__ __forceinline__ void finish_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
+                                           int row,
                                            bool active, bool row_valid, int kwin, int q_abs, int next_q_abs, int sub,
                                            float* sq_out) {
     const int d = p.d;
@@ -160,8 +166,8 @@ __device__ __forceinline__ void finish_row(const EncParams& p, Misc* misc, uint8
                         (float)d * 6.103515625e-5f;
         float delta = 2.1f * E;
         if (force_exact || !isfinite(delta)) delta = __int_as_float(0x7f800000);
-        misc->row_na[row] = na;
-        misc->row_delta[row] = delta;
+        misc->row_na[sl][row] = na;
+        misc->row_delta[sl][row] = delta;
         if (p.dbg_rowscale) p.dbg_rowscale[row] = sa;
     }
     for (int c = sub * 4; c < d; c += 32) {
@@ -202,11 +208,80 @@ struct Top3 {
     }
 };
 
+// 32 accumulator columns of one frame -> three smallest packed (score | column) values.
+// Two scores at a time: sort the pair, then merge it into the sorted triple (8 FMNMX per pair).
+__device__ __forceinline__ void scan32(const uint32_t (&v)[32], const float* __restrict__ nptr, float na, int col0,
+                                       float& m1, float& m2, float& m3, float* dbg) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 nn = __ldg(reinterpret_cast<const float4*>(nptr + j));
+        const float s0 = fmaf(na, nn.x, __uint_as_float(v[j + 0]));
+        const float s1 = fmaf(na, nn.y, __uint_as_float(v[j + 1]));
+        const float s2 = fmaf(na, nn.z, __uint_as_float(v[j + 2]));
+        const float s3 = fmaf(na, nn.w, __uint_as_float(v[j + 3]));
+        if (dbg) {
+            dbg[j + 0] = s0;
+            dbg[j + 1] = s1;
+            dbg[j + 2] = s2;
+            dbg[j + 3] = s3;
+        }
+        const float p0 = __uint_as_float((__float_as_uint(s0) & 0xFFFFFF00u) | (uint32_t)(col0 + j + 0));
+        const float p1 = __uint_as_float((__float_as_uint(s1) & 0xFFFFFF00u) | (uint32_t)(col0 + j + 1));
+        const float p2 = __uint_as_float((__float_as_uint(s2) & 0xFFFFFF00u) | (uint32_t)(col0 + j + 2));
+        const float p3 = __uint_as_float((__float_as_uint(s3) & 0xFFFFFF00u) | (uint32_t)(col0 + j + 3));
+        {
+            const float lo = fminf(p0, p1), hi = fmaxf(p0, p1);
+            const float n3 = fminf(fminf(m3, fmaxf(m2, lo)), fmaxf(m1, hi));
+            const float n2 = fminf(fminf(m2, fmaxf(m1, lo)), hi);
+            m1 = fminf(m1, lo);
+            m2 = n2;
+            m3 = n3;
+        }
+        {
+            const float lo = fminf(p2, p3), hi = fmaxf(p2, p3);
+            const float n3 = fminf(fminf(m3, fmaxf(m2, lo)), fmaxf(m1, hi));
+            const float n2 = fminf(fminf(m2, fmaxf(m1, lo)), hi);
+            m1 = fminf(m1, lo);
+            m2 = n2;
+            m3 = n3;
+        }
+    }
+}
+
+// job = (tile slot, tile, stage); every role walks the same sequence.
+struct JobIter {
+    int n_local, nq, nslots, i, q, slot;  // i = local tile index
+    __device__ __forceinline__ JobIter(int n_local_, int nq_, int nslots_)
+        : n_local(n_local_), nq(nq_), nslots(nslots_), i(0), q(0), slot(0) {}
+    __device__ __forceinline__ bool valid() const { return i < n_local; }
+    __device__ __forceinline__ void next() {
+        // one slot: tile after tile.  two slots: pair p = (2p, 2p+1): for q: (slot0, q), (slot1, q)
+        if (nslots == 1) {
+            if (++q == nq) {
+                q = 0;
+                ++i;
+            }
+            return;
+        }
+        const int pair0 = i & ~1;
+        if (slot == 0 && pair0 + 1 < n_local) {
+            slot = 1;
+            i = pair0 + 1;
+        } else {
+            slot = 0;
+            i = pair0;
+            if (++q == nq) {
+                q = 0;
+                i = pair0 + 2;
+            }
+        }
+    }
+};
+
 template <bool kDebug>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + p.off_B;
     Misc* misc = reinterpret_cast<Misc*>(smem + p.off_misc);
 
@@ -215,6 +290,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     const int n_ks = d / KSLICE;
     const int n_chunks = p.Kpad / CHUNK_N;
     const int nstage = p.nstage;
+    const uint32_t a_tile_bytes = (uint32_t)n_ks * A_SLICE_BYTES;
+    const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nslots = p.nslots;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < nstage; ++i) {
@@ -223,10 +301,11 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&misc->tmem_full[i], 1);
-            mbar_init(&misc->tmem_empty[i], 4);  // one arrive per epilogue warp of the group
+            mbar_init(&misc->tmem_empty[i], 4);  // one arrive per scan warp of the group
+            mbar_init(&misc->a_ready[i], UPD_THREADS);
+            mbar_init(&misc->scan_done[i], SCAN_THREADS);
+            misc->dirty_count[i] = 0;
         }
-        mbar_init(&misc->a_ready, 1);
-        misc->dirty_count = 0;
         for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
         fence_mbar_init();
     }
@@ -241,17 +320,15 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         // =========================================================== TMA producer (codebook slices)
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                for (int q = 0; q < nq; ++q) {
-                    const int row0 = (p.q_begin + q) * p.Kpad;
-                    for (int c = 0; c < n_chunks; ++c) {
-                        for (int ks = 0; ks < n_ks; ++ks, ++it) {
-                            const uint32_t s = it % nstage, ph = (it / nstage) & 1;
-                            mbar_wait(&misc->empty[s], ph ^ 1);
-                            mbar_arrive_expect_tx(&misc->full[s], B_STAGE_BYTES);
-                            tma_load_2d(smem_b + (size_t)s * B_STAGE_BYTES, &tmap_b, &misc->full[s], ks * KSLICE,
-                                        row0 + c * CHUNK_N);
-                        }
+            for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+                const int row0 = (p.q_begin + job.q) * p.Kpad;
+                for (int c = 0; c < n_chunks; ++c) {
+                    for (int ks = 0; ks < n_ks; ++ks, ++it) {
+                        const uint32_t s = it % nstage, ph = (it / nstage) & 1;
+                        mbar_wait(&misc->empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&misc->full[s], B_STAGE_BYTES);
+                        tma_load_2d(smem_b + (size_t)s * B_STAGE_BYTES, &tmap_b, &misc->full[s], ks * KSLICE,
+                                    row0 + c * CHUNK_N);
                     }
                 }
             }
@@ -259,61 +336,154 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     } else if (warp == 1) {
         // =========================================================== MMA issuer
         const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CHUNK_N);
-        uint32_t it = 0, g = 0, astage = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            for (int q = 0; q < nq; ++q) {
-                mbar_wait(&misc->a_ready, astage & 1);
-                ++astage;
+        uint32_t it = 0, g = 0, aphase[2] = {0, 0};
+        for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+            const int sl = job.slot % nslots;
+            mbar_wait(&misc->a_ready[sl], aphase[sl] & 1);
+            ++aphase[sl];
+            tc_fence_after_sync();
+            const uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                const uint32_t buf = g & 1, use = g >> 1;
+                mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
                 tc_fence_after_sync();
-                for (int c = 0; c < n_chunks; ++c, ++g) {
-                    const uint32_t buf = g & 1, use = g >> 1;
-                    mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
+                const uint32_t tmem_d = tmem_base + buf * CHUNK_N;
+                for (int ks = 0; ks < n_ks; ++ks, ++it) {
+                    const uint32_t s = it % nstage, ph = (it / nstage) & 1;
+                    mbar_wait(&misc->full[s], ph);
                     tc_fence_after_sync();
-                    const uint32_t tmem_d = tmem_base + buf * CHUNK_N;
-                    for (int ks = 0; ks < n_ks; ++ks, ++it) {
-                        const uint32_t s = it % nstage, ph = (it / nstage) & 1;
-                        mbar_wait(&misc->full[s], ph);
-                        tc_fence_after_sync();
-                        if (lane == 0) {
-                            const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + (size_t)ks * A_SLICE_BYTES));
-                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)s * B_STAGE_BYTES));
+                    if (lane == 0) {
+                        const uint64_t adesc = umma_desc_sw128(smem_u32(a_tile + (size_t)ks * A_SLICE_BYTES));
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)s * B_STAGE_BYTES));
 #pragma unroll
-                            for (int k16 = 0; k16 < KSLICE / 16; ++k16) {
-                                // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
-                                umma_f16_ss(tmem_d, adesc + (uint64_t)(k16 * 2), bdesc + (uint64_t)(k16 * 2), idesc,
-                                            (ks | k16) != 0);
-                            }
-                            umma_commit(&misc->empty[s]);  // frees the ring slot when these MMAs retire
-                            if (ks == n_ks - 1) umma_commit(&misc->tmem_full[buf]);
+                        for (int k16 = 0; k16 < KSLICE / 16; ++k16) {
+                            // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
+                            umma_f16_ss(tmem_d, adesc + (uint64_t)(k16 * 2), bdesc + (uint64_t)(k16 * 2), idesc,
+                                        (ks | k16) != 0);
                         }
-                        __syncwarp();
+                        umma_commit(&misc->empty[s]);  // frees the ring slot when these MMAs retire
+                        if (ks == n_ks - 1) umma_commit(&misc->tmem_full[buf]);
                     }
+                    __syncwarp();
                 }
             }
         }
-    } else if (warp >= EPI_WARP0) {
-        // =========================================================== epilogue groups
-        const int e = threadIdx.x - EPI_WARP0 * 32;  // 0..255
-        const int grp = e >> 7;                      // epilogue group = accumulator buffer
-        const int my_row = (warp & 3) * 32 + lane;   // TMEM lane owned by this thread
-        const int sub = e & 7, slot = e >> 3;        // 8-lane groups for the cooperative phase
-        const int ewarp = e >> 5;                    // 0..7
-        RTile rt;
-        if (p.r_in_smem) {
-            rt.base = reinterpret_cast<float*>(smem + p.off_R);
-        } else {
-            rt.base = p.r_scratch + (size_t)blockIdx.x * TILE_M * p.r_pitch;
+    } else if (warp >= SCAN_WARP0 && warp < UPD_WARP0) {
+        // =========================================================== scan groups (argmin epilogue)
+        const int e = threadIdx.x - SCAN_WARP0 * 32;  // 0..255
+        const int grp = e >> 7;                       // scan group = accumulator buffer
+        const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
+        uint32_t g = 0, aphase[2] = {0, 0};
+        long long t_scan = 0, t_wait = 0;
+        for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+            const int sl = job.slot % nslots;
+            const int q_abs = p.q_begin + job.q;
+            long long t0 = clock64();
+            mbar_wait(&misc->a_ready[sl], aphase[sl] & 1);  // row constants of this job are visible
+            ++aphase[sl];
+            const float na = misc->row_na[sl][my_row];
+            const float delta = misc->row_delta[sl][my_row];
+            const float* nrm_q = p.cb_norm + (size_t)q_abs * p.Kpad;
+            Top3 G;
+            G.reset();
+            long long t1 = clock64();
+            t_wait += t1 - t0;
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                if ((int)(g & 1) != grp) continue;
+                mbar_wait(&misc->tmem_full[grp], (g >> 1) & 1);
+                tc_fence_after_sync();
+                float m1 = BIG, m2 = BIG, m3 = BIG;
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CHUNK_N;
+                const float* nptr = nrm_q + c * CHUNK_N;
+                float* dbg = nullptr;
+                if (kDebug && p.dbg_scores && job.i == 0 && job.q == 0)
+                    dbg = p.dbg_scores + (size_t)my_row * p.Kpad + c * CHUNK_N;
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(taddr, va);
+#pragma unroll
+                for (int cb = 0; cb < CHUNK_N / 32; cb += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_32x32(taddr + (cb + 1) * 32, vb);
+                    scan32(va, nptr + cb * 32, na, cb * 32, m1, m2, m3, kDebug && dbg ? dbg + cb * 32 : nullptr);
+                    tmem_ld_wait();
+                    if (cb + 2 < CHUNK_N / 32) tmem_ld_32x32(taddr + (cb + 2) * 32, va);
+                    scan32(vb, nptr + (cb + 1) * 32, na, (cb + 1) * 32, m1, m2, m3,
+                           kDebug && dbg ? dbg + (cb + 1) * 32 : nullptr);
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&misc->tmem_empty[grp]);
+                // chunk-local best three -> running best of the stage (values with the column bits cleared)
+                const uint32_t b1 = __float_as_uint(m1), b2 = __float_as_uint(m2), b3 = __float_as_uint(m3);
+                G.insert(__uint_as_float(b1 & 0xFFFFFF00u), c * CHUNK_N + (int)(b1 & 0xFFu));
+                G.insert(__uint_as_float(b2 & 0xFFFFFF00u), c * CHUNK_N + (int)(b2 & 0xFFu));
+                G.v3 = fminf(G.v3, __uint_as_float(b3 & 0xFFFFFF00u));
+            }
+            // ---------------- merge the two groups' candidates, decide how many need an exact score
+            if (grp == 1) {
+                misc->mrg_v[0][my_row] = G.v1;
+                misc->mrg_v[1][my_row] = G.v2;
+                misc->mrg_v[2][my_row] = G.v3;
+                misc->mrg_k[0][my_row] = G.k1;
+                misc->mrg_k[1][my_row] = G.k2;
+            }
+            named_bar_sync(BAR_SCAN, SCAN_THREADS);
+            if (grp == 0) {
+                G.insert(misc->mrg_v[0][my_row], misc->mrg_k[0][my_row]);
+                G.insert(misc->mrg_v[1][my_row], misc->mrg_k[1][my_row]);
+                G.v3 = fminf(G.v3, misc->mrg_v[2][my_row]);
+                const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
+                int nc;
+                const float lim = G.v1 + delta;
+                if (!(G.v1 < BIG) || G.k1 >= Kv || !(lim == lim)) {
+                    nc = 3;  // no usable filter result (NaN / overflow): exact scan
+                } else if (G.v2 > lim) {
+                    nc = 1;
+                } else if (G.v3 > lim && G.k2 < Kv) {
+                    nc = 2;
+                } else {
+                    nc = 3;
+                }
+                misc->cand1[sl][my_row] = G.k1;
+                misc->cand2[sl][my_row] = G.k2;
+                misc->ncand[sl][my_row] = nc;
+                if (nc == 3) {
+                    const int pos = atomicAdd(&misc->dirty_count[sl], 1);
+                    misc->dirty_rows[sl][pos] = my_row;
+                }
+            }
+            named_bar_sync(BAR_SCAN, SCAN_THREADS);  // mrg buffers may be rewritten by the next job
+            mbar_arrive(&misc->scan_done[sl]);
+            t_scan += clock64() - t1;
         }
-        rt.pitch = p.r_pitch;
+        if (p.prof && e == 0) {
+            atomicAdd(p.prof + 0, (unsigned long long)t_scan);
+            atomicAdd(p.prof + 1, (unsigned long long)t_wait);
+        }
+    } else if (warp >= UPD_WARP0) {
+        // =========================================================== update warps
+        const int u = threadIdx.x - UPD_WARP0 * 32;  // 0..UPD_THREADS-1
+        const int sub = u & 7, slot16 = u >> 3;      // 8-lane group per frame
+        const int uwarp = u >> 5;
+        constexpr int ROWS_PER_PASS = UPD_THREADS / 8;
+        constexpr int UPD_WARPS = UPD_THREADS / 32;
         const bool row_major = (p.ad.sd == 1);
-        uint32_t g = 0;
+        long long t_upd = 0, t_dirty = 0, t_wait = 0;
+        unsigned long long n_dirty_tot = 0, n_two_tot = 0, n_jobs = 0;
 
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        auto rtile = [&](int sl) {
+            RTile rt;
+            rt.base = p.r_scratch + ((size_t)blockIdx.x * 2 + sl) * TILE_M * p.r_pitch;
+            rt.pitch = p.r_pitch;
+            return rt;
+        };
+        // load tile `tile` into slot `sl`: residual <- x, fp16 operand + row constants of stage 0
+        auto load_tile = [&](int sl, int tile) {
+            const RTile rt = rtile(sl);
+            uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
             const long long n0 = (long long)tile * TILE_M;
-            // ---------------- load the frame tile into the residual buffer
             if (row_major) {
-                for (int pass = 0; pass < TILE_M / 32; ++pass) {
-                    const int row = pass * 32 + slot;
+                for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                     const long long n = n0 + row;
                     const float* xr = p.x + (n < p.N ? p.ad.row(n) : 0);
                     for (int c = sub * 4; c < d; c += 32) {
@@ -322,211 +492,157 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         *reinterpret_cast<float4*>(rt.at(row, c)) = v;
                     }
                 }
+                // same 8-lane group re-reads exactly what it wrote: no barrier needed
             } else {
-                const int row = e & (TILE_M - 1);
-                const long long n = n0 + row;
-                const float* xr = p.x + (n < p.N ? p.ad.row(n) : 0);
-                for (int c = e >> 7; c < d; c += EPI_THREADS / TILE_M) {
-                    *rt.at(row, c) = (n < p.N) ? xr[(long long)c * p.ad.sd] : 0.f;
+                for (int row = u; row < TILE_M; row += UPD_THREADS) {
+                    const long long n = n0 + row;
+                    const float* xr = p.x + (n < p.N ? p.ad.row(n) : 0);
+                    for (int c = 0; c < d; ++c) *rt.at(row, c) = (n < p.N) ? xr[(long long)c * p.ad.sd] : 0.f;
                 }
+                named_bar_sync(BAR_UPD, UPD_THREADS);
             }
-            named_bar_sync(BAR_EPI, EPI_THREADS);
-            for (int pass = 0; pass < TILE_M / 32; ++pass) {
-                const int row = pass * 32 + slot;
-                finish_row(p, misc, smem_a, rt, row, true, n0 + row < p.N, -1, 0, p.q_begin, sub, nullptr);
-            }
+            for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS)
+                finish_row(p, misc, a_tile, rt, sl, row, true, n0 + row < p.N, -1, 0, p.q_begin, sub, nullptr);
             fence_proxy_async_smem();
-            named_bar_sync(BAR_EPI, EPI_THREADS);
-            if (e == 0) mbar_arrive(&misc->a_ready);
+            mbar_arrive(&misc->a_ready[sl]);
+        };
 
-            for (int q = 0; q < nq; ++q) {
-                const int q_abs = p.q_begin + q;
-                const float na = misc->row_na[my_row];
-                const float delta = misc->row_delta[my_row];
-                const float* nrm_q = p.cb_norm + (size_t)q_abs * p.Kpad;
-                Top3 G;
-                G.reset();
-                for (int c = 0; c < n_chunks; ++c, ++g) {
-                    if ((int)(g & 1) != grp) continue;
-                    mbar_wait(&misc->tmem_full[grp], (g >> 1) & 1);
-                    tc_fence_after_sync();
-                    float m1 = BIG, m2 = BIG, m3 = BIG;
-                    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CHUNK_N;
-#pragma unroll 1
-                    for (int cb32 = 0; cb32 < CHUNK_N / 32; ++cb32) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(taddr + cb32 * 32, v);
-                        tmem_ld_wait();
-                        const float* nptr = nrm_q + c * CHUNK_N + cb32 * 32;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 nn = __ldg(reinterpret_cast<const float4*>(nptr + j));
-                            const float nv[4] = {nn.x, nn.y, nn.z, nn.w};
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const float s = fmaf(na, nv[t], __uint_as_float(v[j + t]));
-                                if constexpr (kDebug) v[j + t] = __float_as_uint(s);
-                                const float pk =
-                                    __uint_as_float((__float_as_uint(s) & 0xFFFFFF00u) | (uint32_t)(cb32 * 32 + j + t));
-                                const float t_ = fmaxf(m1, pk);
-                                m1 = fminf(m1, pk);
-                                const float u_ = fmaxf(m2, t_);
-                                m2 = fminf(m2, t_);
-                                m3 = fminf(m3, u_);
-                            }
-                        }
-                        if (kDebug && p.dbg_scores && tile == 0 && q == 0) {
-                            float* o = p.dbg_scores + (size_t)my_row * p.Kpad + c * CHUNK_N + cb32 * 32;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
-                        }
-                    }
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&misc->tmem_empty[grp]);
-                    // chunk-local best three -> running best of the stage (values with the column bits cleared)
-                    const uint32_t b1 = __float_as_uint(m1), b2 = __float_as_uint(m2), b3 = __float_as_uint(m3);
-                    G.insert(__uint_as_float(b1 & 0xFFFFFF00u), c * CHUNK_N + (int)(b1 & 0xFFu));
-                    G.insert(__uint_as_float(b2 & 0xFFFFFF00u), c * CHUNK_N + (int)(b2 & 0xFFu));
-                    G.v3 = fminf(G.v3, __uint_as_float(b3 & 0xFFFFFF00u));
-                }
-                // ---------------- merge the two groups' candidates, decide how many need an exact score
-                if (grp == 1) {
-                    misc->mrg_v[0][my_row] = G.v1;
-                    misc->mrg_v[1][my_row] = G.v2;
-                    misc->mrg_v[2][my_row] = G.v3;
-                    misc->mrg_k[0][my_row] = G.k1;
-                    misc->mrg_k[1][my_row] = G.k2;
-                }
-                named_bar_sync(BAR_EPI, EPI_THREADS);
-                if (grp == 0) {
-                    G.insert(misc->mrg_v[0][my_row], misc->mrg_k[0][my_row]);
-                    G.insert(misc->mrg_v[1][my_row], misc->mrg_k[1][my_row]);
-                    G.v3 = fminf(G.v3, misc->mrg_v[2][my_row]);
-                    const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
-                    int nc;
-                    const float lim = G.v1 + delta;
-                    if (!(G.v1 < BIG) || G.k1 >= Kv || !(lim == lim)) {
-                        nc = 3;  // no usable filter result (NaN / overflow): exact scan
-                    } else if (G.v2 > lim) {
-                        nc = 1;
-                    } else if (G.v3 > lim && G.k2 < Kv) {
-                        nc = 2;
-                    } else {
-                        nc = 3;
-                    }
-                    misc->cand1[my_row] = G.k1;
-                    misc->cand2[my_row] = G.k2;
-                    misc->ncand[my_row] = nc;
-                    if (nc == 3) {
-                        const int pos = atomicAdd(&misc->dirty_count, 1);
-                        misc->dirty_rows[pos] = my_row;
-                    }
-                }
-                named_bar_sync(BAR_EPI, EPI_THREADS);
-
-                // ---------------- cooperative phase: exact re-rank, gather, residual update, statistics
-                const int next_q_abs = (q + 1 < nq) ? q_abs + 1 : -1;
-                const float* cbq = p.cb + (size_t)q_abs * p.K * d;
-                for (int pass = 0; pass < TILE_M / 32; ++pass) {
-                    const int row = pass * 32 + slot;
-                    const long long n = n0 + row;
-                    const int nc = misc->ncand[row];
-                    int k1 = misc->cand1[row], k2 = misc->cand2[row];
-                    int kwin = k1;
-                    if (__any_sync(0xffffffffu, nc == 2)) {
-                        if (nc != 2) k1 = k2 = 0;
-                        const float s1 = exact_score8(rt.at(row, 0), cbq + (size_t)k1 * d, d, sub);
-                        const float s2 = exact_score8(rt.at(row, 0), cbq + (size_t)k2 * d, d, sub);
-                        if (nc == 2 && better(s2, k2, s1, k1)) kwin = k2;
-                    }
-                    const bool active = nc != 3;
-                    float sq;
-                    finish_row(p, misc, smem_a, rt, row, active, n < p.N, active ? kwin : 0, q_abs, next_q_abs, sub,
-                               &sq);
-                    if (active && sub == 0 && n < p.N) {
-                        p.idx[n * nq + q] = kwin;
-                        atomicAdd(&misc->commit_acc[q], (double)sq);
-                        if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
-                    }
-                }
-                // ---------------- frames the filter could not certify: exact scan of every code
-                const int n_dirty = misc->dirty_count;  // stable: written before the last barrier
-                if (n_dirty > 0) {
-                    const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
-                    const int per = (Kv + 7) / 8;
-                    for (int i = 0; i < n_dirty; ++i) {
-                        const int row = misc->dirty_rows[i];
-                        const int k0 = min(Kv, ewarp * per), k1 = min(Kv, k0 + per);
-                        const ScoreIdx b = exact_scan_warp(rt.at(row, 0), cbq, d, k0, k1, lane);
-                        if (lane == 0) {
-                            misc->dirty_s[ewarp] = b.s;
-                            misc->dirty_k[ewarp] = b.k;
-                        }
-                        named_bar_sync(BAR_EPI, EPI_THREADS);
-                        if (ewarp == (i & 7)) {
-                            float bs = misc->dirty_s[0];
-                            int bk = misc->dirty_k[0];
-                            for (int w = 1; w < 8; ++w)
-                                if (better(misc->dirty_s[w], misc->dirty_k[w], bs, bk)) {
-                                    bs = misc->dirty_s[w];
-                                    bk = misc->dirty_k[w];
-                                }
-                            if (bk < 0 || bk >= Kv) bk = 0;
-                            const long long n = n0 + row;
-                            float sq;
-                            finish_row(p, misc, smem_a, rt, row, lane < 8, n < p.N, bk, q_abs, next_q_abs, sub, &sq);
-                            if (lane == 0 && n < p.N) {
-                                p.idx[n * nq + q] = bk;
-                                atomicAdd(&misc->commit_acc[q], (double)sq);
-                                if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + bk, 1.f);
-                            }
-                        }
-                        named_bar_sync(BAR_EPI, EPI_THREADS);
-                    }
-                }
-                fence_proxy_async_smem();
-                named_bar_sync(BAR_EPI, EPI_THREADS);
-                if (e == 0) {
-                    misc->dirty_count = 0;
-                    if (next_q_abs >= 0) mbar_arrive(&misc->a_ready);
-                }
-            }
-            // ---------------- xq = x - final residual
-            if (row_major) {
-                for (int pass = 0; pass < TILE_M / 32; ++pass) {
-                    const int row = pass * 32 + slot;
-                    const long long n = n0 + row;
-                    if (n < p.N) {
-                        const long long off = p.ad.row(n);
-                        for (int c = sub * 4; c < d; c += 32) {
-                            const float4 xv = *reinterpret_cast<const float4*>(p.x + off + c);
-                            const float4 rv = *reinterpret_cast<const float4*>(rt.at(row, c));
-                            float4 o;
-                            o.x = xv.x - rv.x;
-                            o.y = xv.y - rv.y;
-                            o.z = xv.z - rv.z;
-                            o.w = xv.w - rv.w;
-                            *reinterpret_cast<float4*>(p.xq + off + c) = o;
-                        }
-                    }
-                }
-            } else {
-                const int row = e & (TILE_M - 1);
+        if (n_local > 0) load_tile(0, blockIdx.x);
+        if (n_local > 1 && nslots > 1) load_tile(1, blockIdx.x + gridDim.x);
+        uint32_t sphase[2] = {0, 0};
+        for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+            const int sl = job.slot % nslots;
+            const int q = job.q, q_abs = p.q_begin + q;
+            const int tile = blockIdx.x + job.i * gridDim.x;
+            const long long n0 = (long long)tile * TILE_M;
+            const RTile rt = rtile(sl);
+            uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
+            long long t0 = clock64();
+            mbar_wait(&misc->scan_done[sl], sphase[sl] & 1);
+            ++sphase[sl];
+            long long t1 = clock64();
+            t_wait += t1 - t0;
+            const int next_q_abs = (q + 1 < nq) ? q_abs + 1 : -1;
+            const float* cbq = p.cb + (size_t)q_abs * p.K * d;
+            // ---------------- exact re-rank, gather, residual update, statistics
+            for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                 const long long n = n0 + row;
-                if (n < p.N) {
-                    const long long off = p.ad.row(n);
-                    for (int c = e >> 7; c < d; c += EPI_THREADS / TILE_M) {
-                        const long long o = off + (long long)c * p.ad.sd;
-                        p.xq[o] = p.x[o] - *rt.at(row, c);
+                const int nc = misc->ncand[sl][row];
+                int k1 = misc->cand1[sl][row], k2 = misc->cand2[sl][row];
+                int kwin = k1;
+                if (__any_sync(0xffffffffu, nc == 2)) {
+                    if (nc != 2) k1 = k2 = 0;
+                    const float* cc[2] = {cbq + (size_t)k1 * d, cbq + (size_t)k2 * d};
+                    float s[2];
+                    exact_score8_n<2>(rt.at(row, 0), cc, d, sub, s);
+                    if (nc == 2 && better(s[1], k2, s[0], k1)) kwin = k2;
+                }
+                const bool active = nc != 3;
+                float sq;
+                finish_row(p, misc, a_tile, rt, sl, row, active, n < p.N, active ? kwin : 0, q_abs, next_q_abs, sub,
+                           &sq);
+                if (active && sub == 0 && n < p.N) {
+                    p.idx[n * nq + q] = kwin;
+                    atomicAdd(&misc->commit_acc[q], (double)sq);
+                    if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
+                }
+                if (p.prof && sub == 0 && nc == 2) ++n_two_tot;
+            }
+            long long t2 = clock64();
+            // ---------------- frames the filter could not certify: exact scan of every code
+            const int n_dirty = misc->dirty_count[sl];
+            if (n_dirty > 0) {
+                const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
+                const int per = (Kv + UPD_WARPS - 1) / UPD_WARPS;
+                for (int i = 0; i < n_dirty; ++i) {
+                    const int row = misc->dirty_rows[sl][i];
+                    const int k0 = min(Kv, uwarp * per), k1 = min(Kv, k0 + per);
+                    const ScoreIdx b = exact_scan_warp(rt.at(row, 0), cbq, d, k0, k1, lane);
+                    if (lane == 0) {
+                        misc->dirty_s[uwarp] = b.s;
+                        misc->dirty_k[uwarp] = b.k;
+                    }
+                    named_bar_sync(BAR_UPD, UPD_THREADS);
+                    if (uwarp == (i % UPD_WARPS)) {
+                        float bs = misc->dirty_s[0];
+                        int bk = misc->dirty_k[0];
+                        for (int w = 1; w < UPD_WARPS; ++w)
+                            if (better(misc->dirty_s[w], misc->dirty_k[w], bs, bk)) {
+                                bs = misc->dirty_s[w];
+                                bk = misc->dirty_k[w];
+                            }
+                        if (bk < 0 || bk >= Kv) bk = 0;
+                        const long long n = n0 + row;
+                        float sq;
+                        finish_row(p, misc, a_tile, rt, sl, row, lane < 8, n < p.N, bk, q_abs, next_q_abs, sub, &sq);
+                        if (lane == 0 && n < p.N) {
+                            p.idx[n * nq + q] = bk;
+                            atomicAdd(&misc->commit_acc[q], (double)sq);
+                            if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + bk, 1.f);
+                        }
+                    }
+                    named_bar_sync(BAR_UPD, UPD_THREADS);
+                }
+                if (u == 0) misc->dirty_count[sl] = 0;
+            }
+            long long t3 = clock64();
+            if (next_q_abs >= 0) {
+                fence_proxy_async_smem();
+                mbar_arrive(&misc->a_ready[sl]);
+            } else {
+                // ---------------- last stage: xq = x - final residual, then the slot takes its next tile
+                named_bar_sync(BAR_UPD, UPD_THREADS);  // dirty rows were finished by other warps
+                if (row_major) {
+                    for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
+                        const long long n = n0 + row;
+                        if (n < p.N) {
+                            const long long off = p.ad.row(n);
+                            for (int c = sub * 4; c < d; c += 32) {
+                                const float4 xv = *reinterpret_cast<const float4*>(p.x + off + c);
+                                const float4 rv = *reinterpret_cast<const float4*>(rt.at(row, c));
+                                float4 o;
+                                o.x = xv.x - rv.x;
+                                o.y = xv.y - rv.y;
+                                o.z = xv.z - rv.z;
+                                o.w = xv.w - rv.w;
+                                *reinterpret_cast<float4*>(p.xq + off + c) = o;
+                            }
+                        }
+                    }
+                } else {
+                    for (int row = u; row < TILE_M; row += UPD_THREADS) {
+                        const long long n = n0 + row;
+                        if (n < p.N) {
+                            const long long off = p.ad.row(n);
+                            for (int c = 0; c < d; ++c) {
+                                const long long o = off + (long long)c * p.ad.sd;
+                                p.xq[o] = p.x[o] - *rt.at(row, c);
+                            }
+                        }
                     }
                 }
+                named_bar_sync(BAR_UPD, UPD_THREADS);  // residual slot is rewritten by the next tile
+                const int next_i = job.i + nslots;
+                if (next_i < n_local) load_tile(sl, blockIdx.x + next_i * gridDim.x);
             }
-            named_bar_sync(BAR_EPI, EPI_THREADS);  // residual buffer is reused by the next tile
+            t_upd += t2 - t1 + (clock64() - t3);
+            t_dirty += t3 - t2;
+            n_dirty_tot += n_dirty;
+            ++n_jobs;
         }
-        if (e < nq) {
-            const double v = misc->commit_acc[e];
-            if (v != 0.0) atomicAdd(p.commit_sq + e, v);
+        if (u < nq) {
+            const double v = misc->commit_acc[u];
+            if (v != 0.0) atomicAdd(p.commit_sq + u, v);
+        }
+        if (p.prof) {
+            if (sub == 0) atomicAdd(p.prof + 6, n_two_tot);
+            if (u == 0) {
+                atomicAdd(p.prof + 2, (unsigned long long)t_upd);
+                atomicAdd(p.prof + 3, (unsigned long long)t_dirty);
+                atomicAdd(p.prof + 4, n_dirty_tot);
+                atomicAdd(p.prof + 5, n_jobs);
+                atomicAdd(p.prof + 7, (unsigned long long)t_wait);
+            }
         }
     }
 
@@ -561,34 +677,30 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 struct SmemPlan {
-    uint32_t off_B, off_R, off_misc, total;
-    int nstage, r_in_smem, r_pitch;
+    uint32_t off_B, off_misc, total;
+    int nstage, nslots;
 };
 
 SmemPlan plan_smem(int d, int smem_max) {
     SmemPlan s{};
     const uint32_t a_bytes = (uint32_t)(d / KSLICE) * A_SLICE_BYTES;
     const uint32_t misc_bytes = (uint32_t)((sizeof(Misc) + 1023) / 1024 * 1024);
-    const uint32_t r_bytes_smem = (uint32_t)TILE_M * (d + 4) * 4;
-    const uint32_t r_aligned = (r_bytes_smem + 1023) / 1024 * 1024;
-    // residual tile in shared memory only if at least 3 ring stages still fit
-    s.r_in_smem = (a_bytes + r_aligned + misc_bytes + 3 * B_STAGE_BYTES + 1024 <= (uint32_t)smem_max) ? 1 : 0;
-    s.r_pitch = s.r_in_smem ? d + 4 : d;
-    s.off_B = a_bytes;
-    const uint32_t fixed = a_bytes + (s.r_in_smem ? r_aligned : 0) + misc_bytes + 1024;
+    // two tiles in flight (ping-pong between scan and update warps) if >= 3 ring stages still fit
+    s.nslots = (2 * a_bytes + misc_bytes + 3 * B_STAGE_BYTES + 1024 <= (uint32_t)smem_max) ? 2 : 1;
+    s.off_B = (uint32_t)s.nslots * a_bytes;
+    const uint32_t fixed = s.off_B + misc_bytes + 1024;
     int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / B_STAGE_BYTES) : 0;
     if (ns > MAX_STAGES_RING) ns = MAX_STAGES_RING;
     s.nstage = ns;
-    s.off_R = s.off_B + (uint32_t)ns * B_STAGE_BYTES;
-    s.off_misc = s.off_R + (s.r_in_smem ? r_aligned : 0);
-    s.total = s.off_misc + misc_bytes + 1024;  // slack for the 1024-byte alignment of the dynamic base
+    s.off_misc = s.off_B + (uint32_t)ns * B_STAGE_BYTES;
+    s.total = s.off_misc + misc_bytes + 1024;
     return s;
 }
 }  // namespace
 
 int rvq_tc_workspace_bytes(int d, int num_sms, size_t* out) {
     // per-CTA residual scratch (used when the tile does not fit in shared memory)
-    *out = (size_t)num_sms * TILE_M * d * sizeof(float) + 256;
+    *out = (size_t)num_sms * 2 * TILE_M * d * sizeof(float) + 256 + 128;
     return RVQ_OK;
 }
 
@@ -649,15 +761,20 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     p.stats_cnt = stats_cnt;
     p.num_tiles = num_tiles;
     p.nstage = sp.nstage;
-    p.r_in_smem = sp.r_in_smem;
-    p.r_pitch = sp.r_pitch;
+    p.nslots = sp.nslots;
+    p.r_pitch = d;
     p.off_B = sp.off_B;
-    p.off_R = sp.off_R;
     p.off_misc = sp.off_misc;
     p.dbg_scores = dbg_scores;
     p.dbg_rowscale = dbg_rowscale;
-    if (!sp.r_in_smem) {
-        const size_t need = (size_t)grid * TILE_M * d * sizeof(float);
+    static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
+    if (want_prof && ws && ws_bytes >= 64) {
+        // counters live in the LAST 64 bytes of the workspace
+        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 64) & ~(size_t)7));
+        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 64, st));
+    }
+    {
+        const size_t need = (size_t)grid * 2 * TILE_M * d * sizeof(float);
         uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
         if (!ws || base + need > reinterpret_cast<uintptr_t>(ws) + ws_bytes) {
             set_error("rvq_encode: workspace too small (%zu bytes given, %zu needed)", ws_bytes, need + 256);

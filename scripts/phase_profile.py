@@ -1,0 +1,40 @@
+"""Per-phase cycle counters of the encode kernel (RVQ_PROFILE=1).  python scripts/phase_profile.py c2"""
+import os
+import sys
+
+os.environ["RVQ_PROFILE"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+from audio_generation_b200 import ResidualQuantizer
+
+name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+wl = bench.WORKLOADS[name]
+nq, K, d, N = wl["nq"], wl["K"], wl["d"], min(wl["frames"], 1 << 18)
+q = ResidualQuantizer(nq, d, "ema", K)
+with torch.no_grad():
+    q.codebooks.copy_(bench.synth_codebooks(nq, K, d))
+q = q.cuda().eval()
+x = torch.randn(N, d, device="cuda")
+for _ in range(3):
+    with torch.no_grad():
+        q(x)
+torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record()
+with torch.no_grad():
+    q(x)
+ev1.record()
+torch.cuda.synchronize()
+ws = q._ws
+prof = ws[(ws.numel() - 64) & ~7:][:64].view(torch.int64).cpu().tolist()
+n = max(prof[5], 1)
+ms = ev0.elapsed_time(ev1)
+ctas = min(148, (N + 127) // 128)
+cyc_total = ms * 1e-3 * 1.965e9 * ctas / n
+print(f"workload {name} N={N} ms={ms:.3f} tile-stages={prof[5]}  wall cycles per tile-stage per CTA ~{cyc_total:.0f} "
+      f"(MMA floor {K * d * 128 // 4096})")
+print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+wait {prof[1]/n:.0f})  update={prof[2]/n:.0f} "
+      f"dirty={prof[3]/n:.0f} (+wait {prof[7]/n:.0f})")
+print(f"dirty rows per tile-stage={prof[4]/n:.3f}  two-candidate rows per tile-stage={prof[6]/n:.2f}")
