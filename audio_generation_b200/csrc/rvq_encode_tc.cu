@@ -69,11 +69,11 @@ struct __align__(16) Misc {
     uint64_t full[MAX_STAGES_RING], empty[MAX_STAGES_RING], tmem_full[2], tmem_empty[2], a_ready[2], scan_done[2];
     uint32_t tmem_base;
     int dirty_count[2];
-    float row_na[2][TILE_M], row_delta[2][TILE_M];      // per tile slot
-    int cand1[2][TILE_M], cand2[2][TILE_M], ncand[2][TILE_M];
+    float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
+    int cand[2][3][TILE_M], ncand[2][TILE_M];
     int dirty_rows[2][TILE_M];
-    float mrg_v[3][TILE_M];
-    int mrg_k[2][TILE_M];
+    float mrg_v[5][TILE_M];
+    int mrg_k[3][TILE_M];
     float dirty_s[8];
     int dirty_k[8];
     double commit_acc[MAX_NQ];
@@ -94,44 +94,99 @@ __device__ __forceinline__ uint32_t a_tile_offset(int row, int col) {
            (((uint32_t)c & 7u) << 1);
 }
 
-// An 8-lane group finishes one frame of one stage: optional r <- r - c_win (+ EMA statistics), squared norm
-// and max of the new residual, the per-row constants and the fp16 operand row of the NEXT stage.
+// per-row constants of the next stage from the new residual's norm and the operand scale
+__device__ __forceinline__ void write_row_consts(const EncParams& p, Misc* misc, int sl, int row, int d, float sq,
+                                                 bool force_exact, int a, int b, float sb, float cnmax) {
+    const float sa = exp2i(a);
+    const float na = exp2i(max(-120, min(120, a - b)));
+    const float rs = sqrtf(sq) * 1.00002f * sa;  // scaled ||r||_2 (upper bound)
+    const float cs = cnmax * sb;                 // scaled max ||c||_2
+    // |approx - exact| (scaled units) <= 2^-9(1+..) rs cs  [fp16 rounding of both operands, Cauchy-Schwarz]
+    //   + 2^-15 |score|                                   [8 low mantissa bits replaced by the column]
+    //   + d 2^-14                                          [fp16 subnormal absolute error, accumulate slack]
+    const float E = 1.02f * 0.001953125f * rs * cs + 3.0517578125e-5f * (na * cs * cs + 2.f * rs * cs) +
+                    (float)d * 6.103515625e-5f;
+    float delta = 2.1f * E;
+    if (force_exact || !isfinite(delta)) delta = __int_as_float(0x7f800000);
+    misc->row_na[sl][row] = na;
+    misc->row_delta[sl][row] = delta;
+    if (p.dbg_rowscale) p.dbg_rowscale[row] = sa;
+}
+
+// operand scale exponent for a row whose entries are bounded by amax_bound, given the stage's b
+__device__ __forceinline__ int pick_row_exp(float amax_bound, int b, bool& force_exact) {
+    int a = b + ROW_OVER_CODE_MAX;
+    if (!isfinite(amax_bound)) force_exact = true;
+    if (amax_bound > 0.f && isfinite(amax_bound)) a = min(a, SCALE_TARGET_EXP - ilog2f_floor(amax_bound));
+    if (a < b - ROW_UNDER_CODE_MAX) force_exact = true;  // frame >= 2^40 x larger than the codes: no fp16 window
+    a = max(a, b - ROW_UNDER_CODE_MAX);
+    return max(-100, min(100, a));
+}
+
+__device__ __forceinline__ void store_a4(uint8_t* smem_a, int row, int c, float4 v, float sa) {
+    const __half2 h01 = __floats2half2_rn(v.x * sa, v.y * sa);
+    const __half2 h23 = __floats2half2_rn(v.z * sa, v.w * sa);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(smem_a + a_tile_offset(row, c)) = pk;
+}
+
+// An 8-lane group applies one stage to one frame in ONE pass over memory:
+//   r <- r - c_win (fp32, residual tile in the L2-resident scratch), EMA statistics of the stage input,
+//   squared norm / max of the new residual, and the fp16 operand row + row constants of the next stage.
+// The operand scale of the next stage is chosen from the bound max|r'| <= amax_in + max|c| (known before
+// the pass), so the converted row is written in the same pass; the error bound uses the exact new norm.
 // All 32 lanes of the warp must call this together (8-lane shuffles with a full mask); `active` gates effects.
-//   kwin < 0      : stage-0 initialisation (no subtraction)
-//   next_stage<0  : last stage (no operand for a next stage)
-__device__ __forceinline__ void finish_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
-                                           int row,
-                                           bool active, bool row_valid, int kwin, int q_abs, int next_q_abs, int sub,
-                                           float* sq_out) {
+//   next_q_abs < 0 : last stage (no operand for a next stage)
+__device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
+                                          int row, bool active, bool row_valid, int kwin, int q_abs, int next_q_abs,
+                                          int sub, float* sq_out) {
     const int d = p.d;
     float sq = 0.f, amax = 0.f;
+    float sa = 0.f, sb = 1.f, cnmax = 0.f;
+    int a = 0, b = 0;
+    bool force_exact = false;
+    if (next_q_abs >= 0) {
+        const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
+        sb = mq[0];
+        cnmax = mq[1];
+        b = ilog2f_floor(sb);
+        const float bound = misc->row_amax[sl][row] + p.cb_meta[(size_t)q_abs * META_STRIDE + 2];
+        a = pick_row_exp(bound, b, force_exact);
+        sa = exp2i(a);
+    }
     if (active) {
-        if (kwin >= 0) {
-            const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d;
-            float* ssum = (p.stats_sum && row_valid) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d : nullptr;
-            for (int c = sub * 4; c < d; c += 32) {
-                float4 rv = *reinterpret_cast<float4*>(rt.at(row, c));
-                const float4 cv = ldg_nc_v4(cw + c);
-                if (ssum) red_add_v4(ssum + c, rv);
-                rv.x -= cv.x;
-                rv.y -= cv.y;
-                rv.z -= cv.z;
-                rv.w -= cv.w;
-                *reinterpret_cast<float4*>(rt.at(row, c)) = rv;
-                sq = fmaf(rv.x, rv.x, sq);
-                sq = fmaf(rv.y, rv.y, sq);
-                sq = fmaf(rv.z, rv.z, sq);
-                sq = fmaf(rv.w, rv.w, sq);
-                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(rv.x), fabsf(rv.y)), fmaxf(fabsf(rv.z), fabsf(rv.w))));
+        const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d;
+        float* ssum = (p.stats_sum && row_valid) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d : nullptr;
+        for (int c0 = sub * 4; c0 < d; c0 += 128) {
+            float4 rv[4], cv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = c0 + i * 32;
+                if (c < d) {
+                    rv[i] = *reinterpret_cast<float4*>(rt.at(row, c));
+                    cv[i] = ldg_nc_v4(cw + c);
+                }
             }
-        } else {
-            for (int c = sub * 4; c < d; c += 32) {
-                const float4 rv = *reinterpret_cast<float4*>(rt.at(row, c));
-                sq = fmaf(rv.x, rv.x, sq);
-                sq = fmaf(rv.y, rv.y, sq);
-                sq = fmaf(rv.z, rv.z, sq);
-                sq = fmaf(rv.w, rv.w, sq);
-                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(rv.x), fabsf(rv.y)), fmaxf(fabsf(rv.z), fabsf(rv.w))));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = c0 + i * 32;
+                if (c < d) {
+                    if (ssum) red_add_v4(ssum + c, rv[i]);
+                    float4 nr;
+                    nr.x = rv[i].x - cv[i].x;
+                    nr.y = rv[i].y - cv[i].y;
+                    nr.z = rv[i].z - cv[i].z;
+                    nr.w = rv[i].w - cv[i].w;
+                    *reinterpret_cast<float4*>(rt.at(row, c)) = nr;
+                    sq = fmaf(nr.x, nr.x, sq);
+                    sq = fmaf(nr.y, nr.y, sq);
+                    sq = fmaf(nr.z, nr.z, sq);
+                    sq = fmaf(nr.w, nr.w, sq);
+                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(nr.x), fabsf(nr.y)), fmaxf(fabsf(nr.z), fabsf(nr.w))));
+                    if (next_q_abs >= 0) store_a4(smem_a, row, c, nr, sa);
+                }
             }
         }
     }
@@ -141,69 +196,88 @@ __device__ __forceinline__ void finish_row(const EncParams& p, Misc* misc, uint8
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     }
     if (sq_out) *sq_out = sq;
-    if (!active || next_q_abs < 0) return;
-
-    // ---- constants + fp16 operand row for the next stage
-    const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
-    const float sb = mq[0];        // 2^b
-    const float cnmax = mq[1];     // max ||c||_2 (upper bound)
-    const int b = ilog2f_floor(sb);
-    int a = b + ROW_OVER_CODE_MAX;
-    bool force_exact = !isfinite(amax) || !isfinite(sq);
-    if (amax > 0.f && isfinite(amax)) a = min(a, SCALE_TARGET_EXP - ilog2f_floor(amax));
-    if (a < b - ROW_UNDER_CODE_MAX) force_exact = true;  // frame >= 2^40 x larger than the codes: no fp16 window
-    a = max(a, b - ROW_UNDER_CODE_MAX);
-    a = max(-100, min(100, a));
-    const float sa = exp2i(a);
-    if (sub == 0) {
-        const float na = exp2i(max(-120, min(120, a - b)));
-        const float rs = sqrtf(sq) * 1.00002f * sa;  // scaled ||r||_2 (upper bound)
-        const float cs = cnmax * sb;                 // scaled max ||c||_2
-        // |approx - exact| (scaled units) <= 2^-9(1+..) rs cs  [fp16 rounding of both operands, Cauchy-Schwarz]
-        //   + 2^-15 |score|                                   [8 low mantissa bits replaced by the column]
-        //   + d 2^-14                                          [fp16 subnormal absolute error, accumulate slack]
-        const float E = 1.02f * 0.001953125f * rs * cs + 3.0517578125e-5f * (na * cs * cs + 2.f * rs * cs) +
-                        (float)d * 6.103515625e-5f;
-        float delta = 2.1f * E;
-        if (force_exact || !isfinite(delta)) delta = __int_as_float(0x7f800000);
-        misc->row_na[sl][row] = na;
-        misc->row_delta[sl][row] = delta;
-        if (p.dbg_rowscale) p.dbg_rowscale[row] = sa;
+    if (active && sub == 0) {
+        misc->row_amax[sl][row] = amax;
+        if (next_q_abs >= 0) {
+            if (!isfinite(sq)) force_exact = true;
+            write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
+        }
     }
-    for (int c = sub * 4; c < d; c += 32) {
-        const float4 rv = *reinterpret_cast<float4*>(rt.at(row, c));
-        const __half2 h01 = __floats2half2_rn(rv.x * sa, rv.y * sa);
-        const __half2 h23 = __floats2half2_rn(rv.z * sa, rv.w * sa);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&h01);
-        pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-        *reinterpret_cast<uint2*>(smem_a + a_tile_offset(row, c)) = pk;
+}
+
+// Stage-0 initialisation of one frame by an 8-lane group: x -> residual scratch, exact max -> operand scale,
+// fp16 operand row and row constants of the first stage.  d <= 512 (16 float4 pieces per lane).
+__device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
+                                         int row, const float* __restrict__ xr, bool row_valid, int sub) {
+    const int d = p.d;
+    float4 v[MAX_D / 32];
+    float sq = 0.f, amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAX_D / 32; ++i) {
+        const int c = sub * 4 + i * 32;
+        if (c < d) {
+            v[i] = row_valid ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(rt.at(row, c)) = v[i];
+            sq = fmaf(v[i].x, v[i].x, sq);
+            sq = fmaf(v[i].y, v[i].y, sq);
+            sq = fmaf(v[i].z, v[i].z, sq);
+            sq = fmaf(v[i].w, v[i].w, sq);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    }
+    const float* mq = p.cb_meta + (size_t)p.q_begin * META_STRIDE;
+    const float sb = mq[0], cnmax = mq[1];
+    const int b = ilog2f_floor(sb);
+    bool force_exact = !isfinite(sq);
+    const int a = pick_row_exp(amax, b, force_exact);
+    const float sa = exp2i(a);
+#pragma unroll
+    for (int i = 0; i < MAX_D / 32; ++i) {
+        const int c = sub * 4 + i * 32;
+        if (c < d) store_a4(smem_a, row, c, v[i], sa);
+    }
+    if (sub == 0) {
+        misc->row_amax[sl][row] = amax;
+        write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
     }
 }
 
 __device__ __forceinline__ bool less_vk(float v, int k, float bv, int bk) { return (v < bv) || (v == bv && k < bk); }
 
-// running best-two (value, code) and third value of one frame
-struct Top3 {
-    float v1, v2, v3;
-    int k1, k2;
+// running best-three (value, code), fourth value and the bound H on codes hidden behind a chunk's third
+struct Top4 {
+    float v1, v2, v3, v4, hid;
+    int k1, k2, k3;
     __device__ __forceinline__ void reset() {
-        v1 = v2 = v3 = BIG;
-        k1 = k2 = 0x7fffffff;
+        v1 = v2 = v3 = v4 = hid = BIG;
+        k1 = k2 = k3 = 0x7fffffff;
     }
     __device__ __forceinline__ void insert(float v, int k) {
         if (less_vk(v, k, v1, k1)) {
+            v4 = v3;
             v3 = v2;
+            k3 = k2;
             v2 = v1;
             k2 = k1;
             v1 = v;
             k1 = k;
         } else if (less_vk(v, k, v2, k2)) {
+            v4 = v3;
             v3 = v2;
+            k3 = k2;
             v2 = v;
             k2 = k;
+        } else if (less_vk(v, k, v3, k3)) {
+            v4 = v3;
+            v3 = v;
+            k3 = k;
         } else {
-            v3 = fminf(v3, v);
+            v4 = fminf(v4, v);
         }
     }
 };
@@ -384,7 +458,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             const float na = misc->row_na[sl][my_row];
             const float delta = misc->row_delta[sl][my_row];
             const float* nrm_q = p.cb_norm + (size_t)q_abs * p.Kpad;
-            Top3 G;
+            Top4 G;
             G.reset();
             long long t1 = clock64();
             t_wait += t1 - t0;
@@ -417,37 +491,50 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 const uint32_t b1 = __float_as_uint(m1), b2 = __float_as_uint(m2), b3 = __float_as_uint(m3);
                 G.insert(__uint_as_float(b1 & 0xFFFFFF00u), c * CHUNK_N + (int)(b1 & 0xFFu));
                 G.insert(__uint_as_float(b2 & 0xFFFFFF00u), c * CHUNK_N + (int)(b2 & 0xFFu));
-                G.v3 = fminf(G.v3, __uint_as_float(b3 & 0xFFFFFF00u));
+                G.insert(__uint_as_float(b3 & 0xFFFFFF00u), c * CHUNK_N + (int)(b3 & 0xFFu));
+                // every code of this chunk that is not one of its three best scores at least its third best
+                G.hid = fminf(G.hid, __uint_as_float(b3 & 0xFFFFFF00u));
             }
             // ---------------- merge the two groups' candidates, decide how many need an exact score
             if (grp == 1) {
                 misc->mrg_v[0][my_row] = G.v1;
                 misc->mrg_v[1][my_row] = G.v2;
                 misc->mrg_v[2][my_row] = G.v3;
+                misc->mrg_v[3][my_row] = G.v4;
+                misc->mrg_v[4][my_row] = G.hid;
                 misc->mrg_k[0][my_row] = G.k1;
                 misc->mrg_k[1][my_row] = G.k2;
+                misc->mrg_k[2][my_row] = G.k3;
             }
             named_bar_sync(BAR_SCAN, SCAN_THREADS);
             if (grp == 0) {
                 G.insert(misc->mrg_v[0][my_row], misc->mrg_k[0][my_row]);
                 G.insert(misc->mrg_v[1][my_row], misc->mrg_k[1][my_row]);
-                G.v3 = fminf(G.v3, misc->mrg_v[2][my_row]);
+                G.insert(misc->mrg_v[2][my_row], misc->mrg_k[2][my_row]);
+                G.v4 = fminf(G.v4, misc->mrg_v[3][my_row]);
+                G.hid = fminf(G.hid, misc->mrg_v[4][my_row]);
                 const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
+                // Certificate: a code can beat the approximate best only if its approximate score is <= lim.
+                // Codes outside the kept triples score >= hid; hid >= v3 always, and hid >= v4 unless the three
+                // best share one chunk.
                 int nc;
                 const float lim = G.v1 + delta;
                 if (!(G.v1 < BIG) || G.k1 >= Kv || !(lim == lim)) {
-                    nc = 3;  // no usable filter result (NaN / overflow): exact scan
+                    nc = 4;  // no usable filter result (NaN / overflow): exact scan
                 } else if (G.v2 > lim) {
                     nc = 1;
                 } else if (G.v3 > lim && G.k2 < Kv) {
                     nc = 2;
-                } else {
+                } else if (G.v4 > lim && G.hid > lim && G.k2 < Kv && G.k3 < Kv) {
                     nc = 3;
+                } else {
+                    nc = 4;
                 }
-                misc->cand1[sl][my_row] = G.k1;
-                misc->cand2[sl][my_row] = G.k2;
+                misc->cand[sl][0][my_row] = G.k1;
+                misc->cand[sl][1][my_row] = G.k2;
+                misc->cand[sl][2][my_row] = G.k3;
                 misc->ncand[sl][my_row] = nc;
-                if (nc == 3) {
+                if (nc == 4) {
                     const int pos = atomicAdd(&misc->dirty_count[sl], 1);
                     misc->dirty_rows[sl][pos] = my_row;
                 }
@@ -482,18 +569,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             const RTile rt = rtile(sl);
             uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
             const long long n0 = (long long)tile * TILE_M;
-            if (row_major) {
-                for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
-                    const long long n = n0 + row;
-                    const float* xr = p.x + (n < p.N ? p.ad.row(n) : 0);
-                    for (int c = sub * 4; c < d; c += 32) {
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (n < p.N) v = *reinterpret_cast<const float4*>(xr + c);
-                        *reinterpret_cast<float4*>(rt.at(row, c)) = v;
-                    }
-                }
-                // same 8-lane group re-reads exactly what it wrote: no barrier needed
-            } else {
+            if (!row_major) {
+                // frames-fastest copy (coalesced along the frame axis of the reference's (B, d, L) storage)
                 for (int row = u; row < TILE_M; row += UPD_THREADS) {
                     const long long n = n0 + row;
                     const float* xr = p.x + (n < p.N ? p.ad.row(n) : 0);
@@ -501,8 +578,11 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 }
                 named_bar_sync(BAR_UPD, UPD_THREADS);
             }
-            for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS)
-                finish_row(p, misc, a_tile, rt, sl, row, true, n0 + row < p.N, -1, 0, p.q_begin, sub, nullptr);
+            for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
+                const long long n = n0 + row;
+                const float* xr = row_major ? p.x + (n < p.N ? p.ad.row(n) : 0) : rt.at(row, 0);
+                init_row(p, misc, a_tile, rt, sl, row, xr, row_major ? n < p.N : true, sub);
+            }
             fence_proxy_async_smem();
             mbar_arrive(&misc->a_ready[sl]);
         };
@@ -528,25 +608,34 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                 const long long n = n0 + row;
                 const int nc = misc->ncand[sl][row];
-                int k1 = misc->cand1[sl][row], k2 = misc->cand2[sl][row];
+                const int k1 = misc->cand[sl][0][row];
                 int kwin = k1;
-                if (__any_sync(0xffffffffu, nc == 2)) {
-                    if (nc != 2) k1 = k2 = 0;
-                    const float* cc[2] = {cbq + (size_t)k1 * d, cbq + (size_t)k2 * d};
-                    float s[2];
-                    exact_score8_n<2>(rt.at(row, 0), cc, d, sub, s);
-                    if (nc == 2 && better(s[1], k2, s[0], k1)) kwin = k2;
+                if (__any_sync(0xffffffffu, nc == 2 || nc == 3)) {
+                    const bool sc = (nc == 2 || nc == 3);
+                    const int c1 = sc ? k1 : 0;
+                    const int c2 = sc ? misc->cand[sl][1][row] : 0;
+                    const int c3 = (nc == 3) ? misc->cand[sl][2][row] : c1;
+                    const float* cc[3] = {cbq + (size_t)c1 * d, cbq + (size_t)c2 * d, cbq + (size_t)c3 * d};
+                    float s[3];
+                    exact_score8_n<3>(rt.at(row, 0), cc, d, sub, s);
+                    if (sc) {
+                        float bs = s[0];
+                        if (better(s[1], c2, bs, kwin)) {
+                            bs = s[1];
+                            kwin = c2;
+                        }
+                        if (nc == 3 && better(s[2], c3, bs, kwin)) kwin = c3;
+                    }
                 }
-                const bool active = nc != 3;
+                const bool active = nc != 4;
                 float sq;
-                finish_row(p, misc, a_tile, rt, sl, row, active, n < p.N, active ? kwin : 0, q_abs, next_q_abs, sub,
-                           &sq);
+                apply_row(p, misc, a_tile, rt, sl, row, active, n < p.N, active ? kwin : 0, q_abs, next_q_abs, sub, &sq);
                 if (active && sub == 0 && n < p.N) {
                     p.idx[n * nq + q] = kwin;
                     atomicAdd(&misc->commit_acc[q], (double)sq);
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
-                if (p.prof && sub == 0 && nc == 2) ++n_two_tot;
+                if (p.prof && sub == 0 && (nc == 2 || nc == 3)) ++n_two_tot;
             }
             long long t2 = clock64();
             // ---------------- frames the filter could not certify: exact scan of every code
@@ -574,7 +663,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         if (bk < 0 || bk >= Kv) bk = 0;
                         const long long n = n0 + row;
                         float sq;
-                        finish_row(p, misc, a_tile, rt, sl, row, lane < 8, n < p.N, bk, q_abs, next_q_abs, sub, &sq);
+                        apply_row(p, misc, a_tile, rt, sl, row, lane < 8, n < p.N, bk, q_abs, next_q_abs, sub, &sq);
                         if (lane == 0 && n < p.N) {
                             p.idx[n * nq + q] = bk;
                             atomicAdd(&misc->commit_acc[q], (double)sq);

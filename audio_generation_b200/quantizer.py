@@ -107,7 +107,7 @@ class _RVQFunction(torch.autograd.Function):
         xq, idx, commit_sq = mod._encode(x, nq, update)
         N = idx.numel() // nq
         w = mod.commitment_weight + (1.0 if mod.quantizer_class == "base" else 0.0)
-        commit = (commit_sq.sum() * (w / (N * mod.dim))).to(torch.float32)
+        commit = (commit_sq.sum() * (w / max(N * mod.dim, 1))).to(torch.float32)
         ctx.mod, ctx.nq = mod, nq
         ctx.save_for_backward(x, idx, codebooks)
         ctx.mark_non_differentiable(idx)
@@ -280,7 +280,7 @@ class ResidualQuantizer(nn.Module):
         xq, idx, commit_sq = self._encode(x, nq, update)
         N = idx.numel() // nq
         w = self.commitment_weight + (1.0 if self.quantizer_class == "base" else 0.0)
-        commit = (commit_sq.sum() * (w / (N * self.dim))).to(torch.float32)
+        commit = (commit_sq.sum() * (w / max(N * self.dim, 1))).to(torch.float32)
         return xq, idx, commit
 
     # ------------------------------------------------------------------ decode side
