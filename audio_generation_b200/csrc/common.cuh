@@ -35,7 +35,10 @@ int cuda_fail(cudaError_t e, const char* what);
     } while (0)
 
 // exponent e such that 2^e <= v < 2^(e+1) for finite v > 0
-__device__ __forceinline__ int ilog2f_floor(float v) { return ilogbf(v); }
+__device__ __forceinline__ int ilog2f_floor(float v) {
+    // exponent field of a positive finite float (subnormals report -127: they are treated as tiny)
+    return ((__float_as_int(v) >> 23) & 0xFF) - 127;
+}
 
 // exact power of two as float for |e| <= 126
 __device__ __forceinline__ float exp2i(int e) { return __int_as_float((e + 127) << 23); }

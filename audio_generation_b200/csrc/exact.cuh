@@ -23,7 +23,34 @@ __device__ __forceinline__ bool better(float s, int k, float bs, int bk) {
     return (s < bs) || (s == bs && k < bk);  // lowest index wins exact ties (torch argmin on CPU)
 }
 
-// r: row vector (generic pointer: shared or global), c[j]: code vectors (global). d % 32 == 0.
+// One segment of NP float4 pieces per lane (NP*32 features) starting at feature p0 (lane offset included).
+template <int NC, int NP>
+__device__ __forceinline__ void exact_seg(const float* __restrict__ r, const float* const* c, int p0, float* dot,
+                                          float* nrm) {
+    float4 rv[NP], cv[NC][NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        rv[i] = *reinterpret_cast<const float4*>(r + p0 + i * 32);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) cv[j][i] = ldg_nc_v4(c[j] + p0 + i * 32);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            dot[j] = fmaf(rv[i].x, cv[j][i].x, dot[j]);
+            dot[j] = fmaf(rv[i].y, cv[j][i].y, dot[j]);
+            dot[j] = fmaf(rv[i].z, cv[j][i].z, dot[j]);
+            dot[j] = fmaf(rv[i].w, cv[j][i].w, dot[j]);
+            nrm[j] = fmaf(cv[j][i].x, cv[j][i].x, nrm[j]);
+            nrm[j] = fmaf(cv[j][i].y, cv[j][i].y, nrm[j]);
+            nrm[j] = fmaf(cv[j][i].z, cv[j][i].z, nrm[j]);
+            nrm[j] = fmaf(cv[j][i].w, cv[j][i].w, nrm[j]);
+        }
+    }
+}
+
+// r: row vector (generic pointer: shared or global), c[j]: code vectors (global). d % 64 == 0.
 // All 8 lanes of the group obtain the same out[j].
 template <int NC>
 __device__ __forceinline__ void exact_score8_n(const float* __restrict__ r, const float* const* c, int d, int sub,
@@ -31,35 +58,10 @@ __device__ __forceinline__ void exact_score8_n(const float* __restrict__ r, cons
     float dot[NC], nrm[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) dot[j] = nrm[j] = 0.f;
-    for (int p0 = sub * 4; p0 < d; p0 += 128) {
-        float4 rv[4], cv[NC][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int p = p0 + i * 32;
-            if (p < d) {
-                rv[i] = *reinterpret_cast<const float4*>(r + p);
-#pragma unroll
-                for (int j = 0; j < NC; ++j) cv[j][i] = ldg_nc_v4(c[j] + p);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int p = p0 + i * 32;
-            if (p < d) {
-#pragma unroll
-                for (int j = 0; j < NC; ++j) {
-                    dot[j] = fmaf(rv[i].x, cv[j][i].x, dot[j]);
-                    dot[j] = fmaf(rv[i].y, cv[j][i].y, dot[j]);
-                    dot[j] = fmaf(rv[i].z, cv[j][i].z, dot[j]);
-                    dot[j] = fmaf(rv[i].w, cv[j][i].w, dot[j]);
-                    nrm[j] = fmaf(cv[j][i].x, cv[j][i].x, nrm[j]);
-                    nrm[j] = fmaf(cv[j][i].y, cv[j][i].y, nrm[j]);
-                    nrm[j] = fmaf(cv[j][i].z, cv[j][i].z, nrm[j]);
-                    nrm[j] = fmaf(cv[j][i].w, cv[j][i].w, nrm[j]);
-                }
-            }
-        }
-    }
+    int p0 = sub * 4;
+#pragma unroll 1
+    for (; p0 + 128 <= d + sub * 4; p0 += 128) exact_seg<NC, 4>(r, c, p0, dot, nrm);
+    if (d & 64) exact_seg<NC, 2>(r, c, p0, dot, nrm);
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
 #pragma unroll
@@ -86,7 +88,8 @@ __device__ __forceinline__ ScoreIdx exact_scan_warp(const float* __restrict__ r,
     const int sub = lane & 7, grp = lane >> 3;
     float bs = __int_as_float(0x7f800000);
     int bk = 0x7fffffff;
-    constexpr int NC = 2;
+    constexpr int NC = 4;
+#pragma unroll 1
     for (int kb = k0; kb < k1; kb += 4 * NC) {
         int k[NC];
         const float* cc[NC];

@@ -132,6 +132,36 @@ __device__ __forceinline__ void store_a4(uint8_t* smem_a, int row, int c, float4
     *reinterpret_cast<uint2*>(smem_a + a_tile_offset(row, c)) = pk;
 }
 
+// NP float4 pieces per lane of one frame: r <- r - c (+ statistics, norms, next operand)
+template <int NP>
+__device__ __forceinline__ void apply_seg(uint8_t* smem_a, const RTile& rt, int row, const float* __restrict__ cw,
+                                          float* __restrict__ ssum, int c0, bool write_a, float sa, float& sq,
+                                          float& amax) {
+    float4 rv[NP], cv[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        rv[i] = *reinterpret_cast<float4*>(rt.at(row, c0 + i * 32));
+        cv[i] = ldg_nc_v4(cw + c0 + i * 32);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const int c = c0 + i * 32;
+        if (ssum) red_add_v4(ssum + c, rv[i]);
+        float4 nr;
+        nr.x = rv[i].x - cv[i].x;
+        nr.y = rv[i].y - cv[i].y;
+        nr.z = rv[i].z - cv[i].z;
+        nr.w = rv[i].w - cv[i].w;
+        *reinterpret_cast<float4*>(rt.at(row, c)) = nr;
+        sq = fmaf(nr.x, nr.x, sq);
+        sq = fmaf(nr.y, nr.y, sq);
+        sq = fmaf(nr.z, nr.z, sq);
+        sq = fmaf(nr.w, nr.w, sq);
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(nr.x), fabsf(nr.y)), fmaxf(fabsf(nr.z), fabsf(nr.w))));
+        if (write_a) store_a4(smem_a, row, c, nr, sa);
+    }
+}
+
 // An 8-lane group applies one stage to one frame in ONE pass over memory:
 //   r <- r - c_win (fp32, residual tile in the L2-resident scratch), EMA statistics of the stage input,
 //   squared norm / max of the new residual, and the fp16 operand row + row constants of the next stage.
@@ -147,7 +177,8 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
     float sa = 0.f, sb = 1.f, cnmax = 0.f;
     int a = 0, b = 0;
     bool force_exact = false;
-    if (next_q_abs >= 0) {
+    const bool write_a = next_q_abs >= 0;
+    if (write_a) {
         const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
         sb = mq[0];
         cnmax = mq[1];
@@ -159,36 +190,10 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
     if (active) {
         const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d;
         float* ssum = (p.stats_sum && row_valid) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d : nullptr;
-        for (int c0 = sub * 4; c0 < d; c0 += 128) {
-            float4 rv[4], cv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = c0 + i * 32;
-                if (c < d) {
-                    rv[i] = *reinterpret_cast<float4*>(rt.at(row, c));
-                    cv[i] = ldg_nc_v4(cw + c);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = c0 + i * 32;
-                if (c < d) {
-                    if (ssum) red_add_v4(ssum + c, rv[i]);
-                    float4 nr;
-                    nr.x = rv[i].x - cv[i].x;
-                    nr.y = rv[i].y - cv[i].y;
-                    nr.z = rv[i].z - cv[i].z;
-                    nr.w = rv[i].w - cv[i].w;
-                    *reinterpret_cast<float4*>(rt.at(row, c)) = nr;
-                    sq = fmaf(nr.x, nr.x, sq);
-                    sq = fmaf(nr.y, nr.y, sq);
-                    sq = fmaf(nr.z, nr.z, sq);
-                    sq = fmaf(nr.w, nr.w, sq);
-                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(nr.x), fabsf(nr.y)), fmaxf(fabsf(nr.z), fabsf(nr.w))));
-                    if (next_q_abs >= 0) store_a4(smem_a, row, c, nr, sa);
-                }
-            }
-        }
+        int c0 = sub * 4;
+#pragma unroll 1
+        for (; c0 + 128 <= d + sub * 4; c0 += 128) apply_seg<4>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
+        if (d & 64) apply_seg<2>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
@@ -198,7 +203,7 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
     if (sq_out) *sq_out = sq;
     if (active && sub == 0) {
         misc->row_amax[sl][row] = amax;
-        if (next_q_abs >= 0) {
+        if (write_a) {
             if (!isfinite(sq)) force_exact = true;
             write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
         }
@@ -206,24 +211,20 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
 }
 
 // Stage-0 initialisation of one frame by an 8-lane group: x -> residual scratch, exact max -> operand scale,
-// fp16 operand row and row constants of the first stage.  d <= 512 (16 float4 pieces per lane).
+// fp16 operand row and row constants of the first stage (two passes: the scale needs the row maximum).
 __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
                                          int row, const float* __restrict__ xr, bool row_valid, int sub) {
     const int d = p.d;
-    float4 v[MAX_D / 32];
     float sq = 0.f, amax = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAX_D / 32; ++i) {
-        const int c = sub * 4 + i * 32;
-        if (c < d) {
-            v[i] = row_valid ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(rt.at(row, c)) = v[i];
-            sq = fmaf(v[i].x, v[i].x, sq);
-            sq = fmaf(v[i].y, v[i].y, sq);
-            sq = fmaf(v[i].z, v[i].z, sq);
-            sq = fmaf(v[i].w, v[i].w, sq);
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-        }
+#pragma unroll 2
+    for (int c = sub * 4; c < d; c += 32) {
+        const float4 v = row_valid ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(rt.at(row, c)) = v;
+        sq = fmaf(v.x, v.x, sq);
+        sq = fmaf(v.y, v.y, sq);
+        sq = fmaf(v.z, v.z, sq);
+        sq = fmaf(v.w, v.w, sq);
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
@@ -236,10 +237,10 @@ __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t
     bool force_exact = !isfinite(sq);
     const int a = pick_row_exp(amax, b, force_exact);
     const float sa = exp2i(a);
-#pragma unroll
-    for (int i = 0; i < MAX_D / 32; ++i) {
-        const int c = sub * 4 + i * 32;
-        if (c < d) store_a4(smem_a, row, c, v[i], sa);
+#pragma unroll 2
+    for (int c = sub * 4; c < d; c += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(rt.at(row, c));  // written by this lane above
+        store_a4(smem_a, row, c, v, sa);
     }
     if (sub == 0) {
         misc->row_amax[sl][row] = amax;
@@ -390,7 +391,10 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     tc_fence_after_sync();
     const uint32_t tmem_base = misc->tmem_base;
 
+    // Register budget (512 threads x 128 at launch): the control warpgroup hands registers to the update
+    // warpgroup; each role executes its own setmaxnreg first thing (56*128 + 128*256 + 200*128 = 65536).
     if (warp == 0) {
+        reg_dealloc<56>();
         // =========================================================== TMA producer (codebook slices)
         if (lane == 0) {
             uint32_t it = 0;
@@ -408,13 +412,14 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             }
         }
     } else if (warp == 1) {
+        reg_dealloc<56>();
         // =========================================================== MMA issuer
         const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CHUNK_N);
-        uint32_t it = 0, g = 0, aphase[2] = {0, 0};
+        uint32_t it = 0, g = 0, aphase = 0;
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
             const int sl = job.slot % nslots;
-            mbar_wait(&misc->a_ready[sl], aphase[sl] & 1);
-            ++aphase[sl];
+            mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);
+            aphase ^= 1u << sl;
             tc_fence_after_sync();
             const uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
             for (int c = 0; c < n_chunks; ++c, ++g) {
@@ -442,19 +447,21 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 }
             }
         }
-    } else if (warp >= SCAN_WARP0 && warp < UPD_WARP0) {
+    } else if (warp < SCAN_WARP0) {
+        reg_dealloc<56>();
+    } else if (warp < UPD_WARP0) {
         // =========================================================== scan groups (argmin epilogue)
         const int e = threadIdx.x - SCAN_WARP0 * 32;  // 0..255
         const int grp = e >> 7;                       // scan group = accumulator buffer
         const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
-        uint32_t g = 0, aphase[2] = {0, 0};
+        uint32_t g = 0, aphase = 0;
         long long t_scan = 0, t_wait = 0;
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
             const int sl = job.slot % nslots;
             const int q_abs = p.q_begin + job.q;
             long long t0 = clock64();
-            mbar_wait(&misc->a_ready[sl], aphase[sl] & 1);  // row constants of this job are visible
-            ++aphase[sl];
+            mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);  // row constants of this job are visible
+            aphase ^= 1u << sl;
             const float na = misc->row_na[sl][my_row];
             const float delta = misc->row_delta[sl][my_row];
             const float* nrm_q = p.cb_norm + (size_t)q_abs * p.Kpad;
@@ -547,7 +554,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             atomicAdd(p.prof + 0, (unsigned long long)t_scan);
             atomicAdd(p.prof + 1, (unsigned long long)t_wait);
         }
-    } else if (warp >= UPD_WARP0) {
+    } else {
+        reg_alloc<200>();
         // =========================================================== update warps
         const int u = threadIdx.x - UPD_WARP0 * 32;  // 0..UPD_THREADS-1
         const int sub = u & 7, slot16 = u >> 3;      // 8-lane group per frame
@@ -555,8 +563,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         constexpr int ROWS_PER_PASS = UPD_THREADS / 8;
         constexpr int UPD_WARPS = UPD_THREADS / 32;
         const bool row_major = (p.ad.sd == 1);
-        long long t_upd = 0, t_dirty = 0, t_wait = 0;
-        unsigned long long n_dirty_tot = 0, n_two_tot = 0, n_jobs = 0;
+        long long t_upd = 0, t_dirty = 0, t_wait = 0, t_score = 0, t_apply = 0;
+        unsigned long long n_dirty_tot = 0, n_two_tot = 0, n_jobs = 0, n_score_pass = 0;
+        double commit_local = 0.0;
 
         auto rtile = [&](int sl) {
             RTile rt;
@@ -578,6 +587,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 }
                 named_bar_sync(BAR_UPD, UPD_THREADS);
             }
+#pragma unroll 1
             for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                 const long long n = n0 + row;
                 const float* xr = row_major ? p.x + (n < p.N ? p.ad.row(n) : 0) : rt.at(row, 0);
@@ -589,7 +599,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
 
         if (n_local > 0) load_tile(0, blockIdx.x);
         if (n_local > 1 && nslots > 1) load_tile(1, blockIdx.x + gridDim.x);
-        uint32_t sphase[2] = {0, 0};
+        uint32_t sphase = 0;
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
             const int sl = job.slot % nslots;
             const int q = job.q, q_abs = p.q_begin + q;
@@ -598,19 +608,22 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             const RTile rt = rtile(sl);
             uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
             long long t0 = clock64();
-            mbar_wait(&misc->scan_done[sl], sphase[sl] & 1);
-            ++sphase[sl];
+            mbar_wait(&misc->scan_done[sl], (sphase >> sl) & 1);
+            sphase ^= 1u << sl;
             long long t1 = clock64();
             t_wait += t1 - t0;
             const int next_q_abs = (q + 1 < nq) ? q_abs + 1 : -1;
             const float* cbq = p.cb + (size_t)q_abs * p.K * d;
             // ---------------- exact re-rank, gather, residual update, statistics
+#pragma unroll 1
             for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                 const long long n = n0 + row;
                 const int nc = misc->ncand[sl][row];
                 const int k1 = misc->cand[sl][0][row];
                 int kwin = k1;
+                const long long ts0 = clock64();
                 if (__any_sync(0xffffffffu, nc == 2 || nc == 3)) {
+                    ++n_score_pass;
                     const bool sc = (nc == 2 || nc == 3);
                     const int c1 = sc ? k1 : 0;
                     const int c2 = sc ? misc->cand[sl][1][row] : 0;
@@ -629,20 +642,27 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 }
                 const bool active = nc != 4;
                 float sq;
+                const long long ts1 = clock64();
                 apply_row(p, misc, a_tile, rt, sl, row, active, n < p.N, active ? kwin : 0, q_abs, next_q_abs, sub, &sq);
+                const long long ts2 = clock64();
                 if (active && sub == 0 && n < p.N) {
                     p.idx[n * nq + q] = kwin;
-                    atomicAdd(&misc->commit_acc[q], (double)sq);
+                    commit_local += (double)sq;
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
+                t_score += ts1 - ts0;
+                t_apply += ts2 - ts1;
                 if (p.prof && sub == 0 && (nc == 2 || nc == 3)) ++n_two_tot;
             }
+            if (sub == 0 && commit_local != 0.0) atomicAdd(&misc->commit_acc[q], commit_local);
+            commit_local = 0.0;
             long long t2 = clock64();
             // ---------------- frames the filter could not certify: exact scan of every code
             const int n_dirty = misc->dirty_count[sl];
             if (n_dirty > 0) {
                 const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
                 const int per = (Kv + UPD_WARPS - 1) / UPD_WARPS;
+#pragma unroll 1
                 for (int i = 0; i < n_dirty; ++i) {
                     const int row = misc->dirty_rows[sl][i];
                     const int k0 = min(Kv, uwarp * per), k1 = min(Kv, k0 + per);
@@ -682,6 +702,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 // ---------------- last stage: xq = x - final residual, then the slot takes its next tile
                 named_bar_sync(BAR_UPD, UPD_THREADS);  // dirty rows were finished by other warps
                 if (row_major) {
+#pragma unroll 1
                     for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                         const long long n = n0 + row;
                         if (n < p.N) {
@@ -731,6 +752,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 atomicAdd(p.prof + 4, n_dirty_tot);
                 atomicAdd(p.prof + 5, n_jobs);
                 atomicAdd(p.prof + 7, (unsigned long long)t_wait);
+                atomicAdd(p.prof + 8, (unsigned long long)t_score);
+                atomicAdd(p.prof + 9, (unsigned long long)t_apply);
+                atomicAdd(p.prof + 10, n_score_pass);
             }
         }
     }
@@ -789,7 +813,7 @@ SmemPlan plan_smem(int d, int smem_max) {
 
 int rvq_tc_workspace_bytes(int d, int num_sms, size_t* out) {
     // per-CTA residual scratch (used when the tile does not fit in shared memory)
-    *out = (size_t)num_sms * 2 * TILE_M * d * sizeof(float) + 256 + 128;
+    *out = (size_t)num_sms * 2 * TILE_M * d * sizeof(float) + 256 + 256;
     return RVQ_OK;
 }
 
@@ -857,10 +881,10 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     p.dbg_scores = dbg_scores;
     p.dbg_rowscale = dbg_rowscale;
     static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
-    if (want_prof && ws && ws_bytes >= 64) {
-        // counters live in the LAST 64 bytes of the workspace
-        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 64) & ~(size_t)7));
-        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 64, st));
+    if (want_prof && ws && ws_bytes >= 128) {
+        // counters live in the LAST 128 bytes of the workspace
+        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 128) & ~(size_t)7));
+        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 128, st));
     }
     {
         const size_t need = (size_t)grid * 2 * TILE_M * d * sizeof(float);

@@ -28,7 +28,7 @@ with torch.no_grad():
 ev1.record()
 torch.cuda.synchronize()
 ws = q._ws
-prof = ws[(ws.numel() - 64) & ~7:][:64].view(torch.int64).cpu().tolist()
+prof = ws[(ws.numel() - 128) & ~7:][:128].view(torch.int64).cpu().tolist()
 n = max(prof[5], 1)
 ms = ev0.elapsed_time(ev1)
 ctas = min(148, (N + 127) // 128)
@@ -37,4 +37,5 @@ print(f"workload {name} N={N} ms={ms:.3f} tile-stages={prof[5]}  wall cycles per
       f"(MMA floor {K * d * 128 // 4096})")
 print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+wait {prof[1]/n:.0f})  update={prof[2]/n:.0f} "
       f"dirty={prof[3]/n:.0f} (+wait {prof[7]/n:.0f})")
+print(f"  update breakdown per tile-stage (thread 0): score={prof[8]/n:.0f} apply={prof[9]/n:.0f} score-passes={prof[10]/n:.2f}")
 print(f"dirty rows per tile-stage={prof[4]/n:.3f}  two-candidate rows per tile-stage={prof[6]/n:.2f}")
