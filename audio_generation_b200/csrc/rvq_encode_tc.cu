@@ -72,6 +72,8 @@ struct __align__(16) Misc {
     float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
     int cand[2][3][TILE_M], ncand[2][TILE_M];
     int dirty_rows[2][TILE_M];
+    int score_rows[2][TILE_M];
+    int score_count[2];
     float mrg_v[5][TILE_M];
     int mrg_k[3][TILE_M];
     float dirty_s[8];
@@ -210,6 +212,82 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
     }
 }
 
+// Batched form of apply_row for d = 128 * SEGS: RB frames per 8-lane group with every load of the batch
+// issued before the first dependent instruction (one L2 round trip per batch instead of one per frame).
+// Inactive frames (exact-scan fallback pending) load harmlessly and store nothing.
+template <int RB, int SEGS>
+__device__ __forceinline__ void apply_rows(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
+                                           const int* rows, const bool* active, const bool* row_valid,
+                                           const int* kwin, int q_abs, int next_q_abs, int sub, float* sq_out) {
+    constexpr int d = 128 * SEGS;
+    const bool write_a = next_q_abs >= 0;
+    float sb = 1.f, cnmax = 0.f, cmax_q = 0.f;
+    int b = 0;
+    if (write_a) {
+        const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
+        sb = mq[0];
+        cnmax = mq[1];
+        b = ilog2f_floor(sb);
+        cmax_q = p.cb_meta[(size_t)q_abs * META_STRIDE + 2];
+    }
+    float4 rv[RB][SEGS * 4], cv[RB][SEGS * 4];
+    const float* cw[RB];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+        cw[j] = p.cb + ((size_t)q_abs * p.K + kwin[j]) * d;
+#pragma unroll
+        for (int i = 0; i < SEGS * 4; ++i) {
+            rv[j][i] = *reinterpret_cast<float4*>(rt.at(rows[j], sub * 4 + i * 32));
+            cv[j][i] = ldg_nc_v4(cw[j] + sub * 4 + i * 32);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+        int a = 0;
+        float sa = 0.f;
+        bool force_exact = false;
+        if (write_a) {
+            a = pick_row_exp(misc->row_amax[sl][rows[j]] + cmax_q, b, force_exact);
+            sa = exp2i(a);
+        }
+        float sq = 0.f, amax = 0.f;
+        float* ssum = (p.stats_sum && row_valid[j] && active[j]) ? p.stats_sum + ((size_t)q_abs * p.K + kwin[j]) * d
+                                                                 : nullptr;
+#pragma unroll
+        for (int i = 0; i < SEGS * 4; ++i) {
+            const int c = sub * 4 + i * 32;
+            if (ssum) red_add_v4(ssum + c, rv[j][i]);
+            float4 nr;
+            nr.x = rv[j][i].x - cv[j][i].x;
+            nr.y = rv[j][i].y - cv[j][i].y;
+            nr.z = rv[j][i].z - cv[j][i].z;
+            nr.w = rv[j][i].w - cv[j][i].w;
+            if (active[j]) {
+                *reinterpret_cast<float4*>(rt.at(rows[j], c)) = nr;
+                if (write_a) store_a4(smem_a, rows[j], c, nr, sa);
+            }
+            sq = fmaf(nr.x, nr.x, sq);
+            sq = fmaf(nr.y, nr.y, sq);
+            sq = fmaf(nr.z, nr.z, sq);
+            sq = fmaf(nr.w, nr.w, sq);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(nr.x), fabsf(nr.y)), fmaxf(fabsf(nr.z), fabsf(nr.w))));
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        }
+        sq_out[j] = sq;
+        if (active[j] && sub == 0) {
+            misc->row_amax[sl][rows[j]] = amax;
+            if (write_a) {
+                if (!isfinite(sq)) force_exact = true;
+                write_row_consts(p, misc, sl, rows[j], d, sq, force_exact, a, b, sb, cnmax);
+            }
+        }
+    }
+}
+
 // Stage-0 initialisation of one frame by an 8-lane group: x -> residual scratch, exact max -> operand scale,
 // fp16 operand row and row constants of the first stage (two passes: the scale needs the row maximum).
 __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
@@ -300,10 +378,11 @@ __device__ __forceinline__ void scan32(const uint32_t (&v)[32], const float* __r
             dbg[j + 2] = s2;
             dbg[j + 3] = s3;
         }
-        const float p0 = __uint_as_float((__float_as_uint(s0) & 0xFFFFFF00u) | (uint32_t)(col0 + j + 0));
-        const float p1 = __uint_as_float((__float_as_uint(s1) & 0xFFFFFF00u) | (uint32_t)(col0 + j + 1));
-        const float p2 = __uint_as_float((__float_as_uint(s2) & 0xFFFFFF00u) | (uint32_t)(col0 + j + 2));
-        const float p3 = __uint_as_float((__float_as_uint(s3) & 0xFFFFFF00u) | (uint32_t)(col0 + j + 3));
+        // low mantissa byte <- column (one PRMT): the packed value orders by score first, column second
+        const float p0 = __uint_as_float(__byte_perm(__float_as_uint(s0), (uint32_t)(col0 + j + 0), 0x3214));
+        const float p1 = __uint_as_float(__byte_perm(__float_as_uint(s1), (uint32_t)(col0 + j + 1), 0x3214));
+        const float p2 = __uint_as_float(__byte_perm(__float_as_uint(s2), (uint32_t)(col0 + j + 2), 0x3214));
+        const float p3 = __uint_as_float(__byte_perm(__float_as_uint(s3), (uint32_t)(col0 + j + 3), 0x3214));
         {
             const float lo = fminf(p0, p1), hi = fmaxf(p0, p1);
             const float n3 = fminf(fminf(m3, fmaxf(m2, lo)), fmaxf(m1, hi));
@@ -380,6 +459,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             mbar_init(&misc->a_ready[i], UPD_THREADS);
             mbar_init(&misc->scan_done[i], SCAN_THREADS);
             misc->dirty_count[i] = 0;
+            misc->score_count[i] = 0;
         }
         for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
         fence_mbar_init();
@@ -455,7 +535,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         const int grp = e >> 7;                       // scan group = accumulator buffer
         const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
         uint32_t g = 0, aphase = 0;
-        long long t_scan = 0, t_wait = 0;
+        long long t_scan = 0, t_wait = 0, t_full = 0;
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
             const int sl = job.slot % nslots;
             const int q_abs = p.q_begin + job.q;
@@ -471,8 +551,10 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             t_wait += t1 - t0;
             for (int c = 0; c < n_chunks; ++c, ++g) {
                 if ((int)(g & 1) != grp) continue;
+                const long long tw0 = clock64();
                 mbar_wait(&misc->tmem_full[grp], (g >> 1) & 1);
                 tc_fence_after_sync();
+                t_full += clock64() - tw0;
                 float m1 = BIG, m2 = BIG, m3 = BIG;
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CHUNK_N;
                 const float* nptr = nrm_q + c * CHUNK_N;
@@ -544,6 +626,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 if (nc == 4) {
                     const int pos = atomicAdd(&misc->dirty_count[sl], 1);
                     misc->dirty_rows[sl][pos] = my_row;
+                } else if (nc >= 2) {
+                    const int pos = atomicAdd(&misc->score_count[sl], 1);
+                    misc->score_rows[sl][pos] = my_row;
                 }
             }
             named_bar_sync(BAR_SCAN, SCAN_THREADS);  // mrg buffers may be rewritten by the next job
@@ -553,6 +638,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         if (p.prof && e == 0) {
             atomicAdd(p.prof + 0, (unsigned long long)t_scan);
             atomicAdd(p.prof + 1, (unsigned long long)t_wait);
+            atomicAdd(p.prof + 11, (unsigned long long)t_full);
         }
     } else {
         reg_alloc<200>();
@@ -614,46 +700,81 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             t_wait += t1 - t0;
             const int next_q_abs = (q + 1 < nq) ? q_abs + 1 : -1;
             const float* cbq = p.cb + (size_t)q_abs * p.K * d;
-            // ---------------- exact re-rank, gather, residual update, statistics
-#pragma unroll 1
-            for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
-                const long long n = n0 + row;
+            // ---------------- exact re-rank of the frames with 2 or 3 candidates (compacted list)
+            const long long ts0 = clock64();
+            const int n_score = misc->score_count[sl];
+            for (int base = 0; base < n_score; base += ROWS_PER_PASS) {
+                const int i = base + slot16;
+                const bool sc = i < n_score;
+                const int row = misc->score_rows[sl][sc ? i : 0];
                 const int nc = misc->ncand[sl][row];
-                const int k1 = misc->cand[sl][0][row];
-                int kwin = k1;
-                const long long ts0 = clock64();
-                if (__any_sync(0xffffffffu, nc == 2 || nc == 3)) {
-                    ++n_score_pass;
-                    const bool sc = (nc == 2 || nc == 3);
-                    const int c1 = sc ? k1 : 0;
-                    const int c2 = sc ? misc->cand[sl][1][row] : 0;
-                    const int c3 = (nc == 3) ? misc->cand[sl][2][row] : c1;
-                    const float* cc[3] = {cbq + (size_t)c1 * d, cbq + (size_t)c2 * d, cbq + (size_t)c3 * d};
-                    float s[3];
-                    exact_score8_n<3>(rt.at(row, 0), cc, d, sub, s);
-                    if (sc) {
-                        float bs = s[0];
-                        if (better(s[1], c2, bs, kwin)) {
-                            bs = s[1];
-                            kwin = c2;
-                        }
-                        if (nc == 3 && better(s[2], c3, bs, kwin)) kwin = c3;
+                const int c1 = misc->cand[sl][0][row], c2 = misc->cand[sl][1][row];
+                const int c3 = (nc == 3) ? misc->cand[sl][2][row] : c1;
+                const float* cc[3] = {cbq + (size_t)c1 * d, cbq + (size_t)c2 * d, cbq + (size_t)c3 * d};
+                float s[3];
+                exact_score8_n<3>(rt.at(row, 0), cc, d, sub, s);
+                if (sc && sub == 0) {
+                    float bs = s[0];
+                    int kwin = c1;
+                    if (better(s[1], c2, bs, kwin)) {
+                        bs = s[1];
+                        kwin = c2;
                     }
+                    if (nc == 3 && better(s[2], c3, bs, kwin)) kwin = c3;
+                    misc->cand[sl][0][row] = kwin;
                 }
-                const bool active = nc != 4;
-                float sq;
-                const long long ts1 = clock64();
-                apply_row(p, misc, a_tile, rt, sl, row, active, n < p.N, active ? kwin : 0, q_abs, next_q_abs, sub, &sq);
-                const long long ts2 = clock64();
+                ++n_score_pass;
+            }
+            if (n_score > 0) named_bar_sync(BAR_UPD, UPD_THREADS);  // winners visible to the applying groups
+            n_two_tot += n_score;
+            const long long ts1 = clock64();
+            // ---------------- gather, residual update, statistics, next operand
+            auto post_row = [&](int row, bool active, int kwin, float sq) {
+                const long long n = n0 + row;
                 if (active && sub == 0 && n < p.N) {
                     p.idx[n * nq + q] = kwin;
                     commit_local += (double)sq;
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
-                t_score += ts1 - ts0;
-                t_apply += ts2 - ts1;
-                if (p.prof && sub == 0 && (nc == 2 || nc == 3)) ++n_two_tot;
+            };
+            if (d == 128 || d == 256 || d == 512) {
+                constexpr int RB_MAX = 4;
+                const int rb = d == 128 ? 4 : (d == 256 ? 2 : 1);
+#pragma unroll 1
+                for (int r0 = slot16; r0 < TILE_M; r0 += ROWS_PER_PASS * rb) {
+                    int rows[RB_MAX], kwin[RB_MAX];
+                    bool active[RB_MAX], valid[RB_MAX];
+                    float sq[RB_MAX];
+#pragma unroll
+                    for (int j = 0; j < RB_MAX; ++j) {
+                        rows[j] = r0 + (j < rb ? j : 0) * ROWS_PER_PASS;
+                        active[j] = misc->ncand[sl][rows[j]] != 4;
+                        kwin[j] = active[j] ? misc->cand[sl][0][rows[j]] : 0;
+                        valid[j] = n0 + rows[j] < p.N;
+                    }
+                    if (d == 128)
+                        apply_rows<4, 1>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
+                    else if (d == 256)
+                        apply_rows<2, 2>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
+                    else
+                        apply_rows<1, 4>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
+#pragma unroll
+                    for (int j = 0; j < RB_MAX; ++j)
+                        if (j < rb) post_row(rows[j], active[j], kwin[j], sq[j]);
+                }
+            } else {
+#pragma unroll 1
+                for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
+                    const bool active = misc->ncand[sl][row] != 4;
+                    const int kwin = active ? misc->cand[sl][0][row] : 0;
+                    float sq;
+                    apply_row(p, misc, a_tile, rt, sl, row, active, n0 + row < p.N, kwin, q_abs, next_q_abs, sub, &sq);
+                    post_row(row, active, kwin, sq);
+                }
             }
+            const long long ts2 = clock64();
+            t_score += ts1 - ts0;
+            t_apply += ts2 - ts1;
             if (sub == 0 && commit_local != 0.0) atomicAdd(&misc->commit_acc[q], commit_local);
             commit_local = 0.0;
             long long t2 = clock64();
@@ -694,6 +815,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 }
                 if (u == 0) misc->dirty_count[sl] = 0;
             }
+            if (u == 0) misc->score_count[sl] = 0;
             long long t3 = clock64();
             if (next_q_abs >= 0) {
                 fence_proxy_async_smem();
@@ -745,7 +867,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             if (v != 0.0) atomicAdd(p.commit_sq + u, v);
         }
         if (p.prof) {
-            if (sub == 0) atomicAdd(p.prof + 6, n_two_tot);
+            if (u == 0) atomicAdd(p.prof + 6, n_two_tot);
             if (u == 0) {
                 atomicAdd(p.prof + 2, (unsigned long long)t_upd);
                 atomicAdd(p.prof + 3, (unsigned long long)t_dirty);

@@ -37,5 +37,6 @@ print(f"workload {name} N={N} ms={ms:.3f} tile-stages={prof[5]}  wall cycles per
       f"(MMA floor {K * d * 128 // 4096})")
 print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+wait {prof[1]/n:.0f})  update={prof[2]/n:.0f} "
       f"dirty={prof[3]/n:.0f} (+wait {prof[7]/n:.0f})")
+print(f"  scan: of which waiting for the accumulator (tmem_full) = {prof[11]/n:.0f}")
 print(f"  update breakdown per tile-stage (thread 0): score={prof[8]/n:.0f} apply={prof[9]/n:.0f} score-passes={prof[10]/n:.2f}")
 print(f"dirty rows per tile-stage={prof[4]/n:.3f}  two-candidate rows per tile-stage={prof[6]/n:.2f}")
