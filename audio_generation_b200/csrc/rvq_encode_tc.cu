@@ -29,8 +29,8 @@ namespace rvq {
 constexpr int SCAN_WARP0 = 4;
 constexpr int SCAN_THREADS = 256;
 constexpr int UPD_WARP0 = 12;
-constexpr int UPD_THREADS = 128;
-constexpr int NUM_THREADS = UPD_WARP0 * 32 + UPD_THREADS;  // 512
+constexpr int UPD_THREADS = 256;
+constexpr int NUM_THREADS = UPD_WARP0 * 32 + UPD_THREADS;  // 640
 constexpr int MAX_STAGES_RING = 6;
 constexpr int MAX_NQ = 64;
 constexpr uint32_t A_SLICE_BYTES = TILE_M * KSLICE * 2;   // 16 KiB
@@ -361,12 +361,12 @@ struct Top4 {
     }
 };
 
-// 32 accumulator columns of one frame -> three smallest packed (score | column) values.
+// 16 accumulator columns of one frame -> three smallest packed (score | column) values.
 // Two scores at a time: sort the pair, then merge it into the sorted triple (8 FMNMX per pair).
-__device__ __forceinline__ void scan32(const uint32_t (&v)[32], const float* __restrict__ nptr, float na, int col0,
+__device__ __forceinline__ void scan16(const uint32_t (&v)[16], const float* __restrict__ nptr, float na, int col0,
                                        float& m1, float& m2, float& m3, float* dbg) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < 16; j += 4) {
         const float4 nn = __ldg(reinterpret_cast<const float4*>(nptr + j));
         const float s0 = fmaf(na, nn.x, __uint_as_float(v[j + 0]));
         const float s1 = fmaf(na, nn.y, __uint_as_float(v[j + 1]));
@@ -471,10 +471,10 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     tc_fence_after_sync();
     const uint32_t tmem_base = misc->tmem_base;
 
-    // Register budget (512 threads x 128 at launch): the control warpgroup hands registers to the update
-    // warpgroup; each role executes its own setmaxnreg first thing (56*128 + 128*256 + 200*128 = 65536).
+    // Register budget (640 threads x 96 at launch): control and scan warpgroups hand registers to the update
+    // warpgroups; each role executes its own setmaxnreg first thing (40*128 + 88*256 + 144*256 = 64512).
     if (warp == 0) {
-        reg_dealloc<56>();
+        reg_dealloc<40>();
         // =========================================================== TMA producer (codebook slices)
         if (lane == 0) {
             uint32_t it = 0;
@@ -492,7 +492,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             }
         }
     } else if (warp == 1) {
-        reg_dealloc<56>();
+        reg_dealloc<40>();
         // =========================================================== MMA issuer
         const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CHUNK_N);
         uint32_t it = 0, g = 0, aphase = 0;
@@ -528,8 +528,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             }
         }
     } else if (warp < SCAN_WARP0) {
-        reg_dealloc<56>();
+        reg_dealloc<40>();
     } else if (warp < UPD_WARP0) {
+        reg_dealloc<88>();
         // =========================================================== scan groups (argmin epilogue)
         const int e = threadIdx.x - SCAN_WARP0 * 32;  // 0..255
         const int grp = e >> 7;                       // scan group = accumulator buffer
@@ -561,17 +562,18 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 float* dbg = nullptr;
                 if (kDebug && p.dbg_scores && job.i == 0 && job.q == 0)
                     dbg = p.dbg_scores + (size_t)my_row * p.Kpad + c * CHUNK_N;
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32(taddr, va);
-#pragma unroll
-                for (int cb = 0; cb < CHUNK_N / 32; cb += 2) {
+                // 16 columns per TMEM load, double buffered; the loop body (32 columns) stays small enough for
+                // the instruction cache (a fully unrolled 256-column body does not)
+                uint32_t va[16], vb[16];
+                tmem_ld_32x16(taddr, va);
+#pragma unroll 1
+                for (int cb = 0; cb < CHUNK_N; cb += 32) {
                     tmem_ld_wait();
-                    tmem_ld_32x32(taddr + (cb + 1) * 32, vb);
-                    scan32(va, nptr + cb * 32, na, cb * 32, m1, m2, m3, kDebug && dbg ? dbg + cb * 32 : nullptr);
+                    tmem_ld_32x16(taddr + cb + 16, vb);
+                    scan16(va, nptr + cb, na, cb, m1, m2, m3, kDebug && dbg ? dbg + cb : nullptr);
                     tmem_ld_wait();
-                    if (cb + 2 < CHUNK_N / 32) tmem_ld_32x32(taddr + (cb + 2) * 32, va);
-                    scan32(vb, nptr + (cb + 1) * 32, na, (cb + 1) * 32, m1, m2, m3,
-                           kDebug && dbg ? dbg + (cb + 1) * 32 : nullptr);
+                    if (cb + 32 < CHUNK_N) tmem_ld_32x16(taddr + cb + 32, va);
+                    scan16(vb, nptr + cb + 16, na, cb + 16, m1, m2, m3, kDebug && dbg ? dbg + cb + 16 : nullptr);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
@@ -641,7 +643,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             atomicAdd(p.prof + 11, (unsigned long long)t_full);
         }
     } else {
-        reg_alloc<200>();
+        reg_alloc<144>();
         // =========================================================== update warps
         const int u = threadIdx.x - UPD_WARP0 * 32;  // 0..UPD_THREADS-1
         const int sub = u & 7, slot16 = u >> 3;      // 8-lane group per frame
@@ -737,9 +739,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
             };
-            if (d == 128 || d == 256 || d == 512) {
-                constexpr int RB_MAX = 4;
-                const int rb = d == 128 ? 4 : (d == 256 ? 2 : 1);
+            if (d == 128 || d == 256) {
+                constexpr int RB_MAX = 2;
+                const int rb = d == 128 ? 2 : 1;
 #pragma unroll 1
                 for (int r0 = slot16; r0 < TILE_M; r0 += ROWS_PER_PASS * rb) {
                     int rows[RB_MAX], kwin[RB_MAX];
@@ -753,11 +755,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         valid[j] = n0 + rows[j] < p.N;
                     }
                     if (d == 128)
-                        apply_rows<4, 1>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
-                    else if (d == 256)
-                        apply_rows<2, 2>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
+                        apply_rows<2, 1>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
                     else
-                        apply_rows<1, 4>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
+                        apply_rows<1, 2>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
 #pragma unroll
                     for (int j = 0; j < RB_MAX; ++j)
                         if (j < rb) post_row(rows[j], active[j], kwin[j], sq[j]);
