@@ -81,14 +81,14 @@ __device__ __forceinline__ float exact_score8(const float* __restrict__ r, const
     return o[0];
 }
 
-// Exact argmin over codes [k0, k1) for one row by ONE WARP: 4 groups of 8 lanes, 8 codes per group per step
-// (32 codes per warp step, all loads of a step in flight together).  Every lane returns the warp-wide best.
+// Exact argmin over codes [k0, k1) for one row by ONE WARP: 4 groups of 8 lanes, 4 codes per group per step
+// (16 codes per warp step, all loads of a step in flight together).  Every lane returns the warp-wide best.
 __device__ __forceinline__ ScoreIdx exact_scan_warp(const float* __restrict__ r, const float* __restrict__ cbq,
                                                     int d, int k0, int k1, int lane) {
     const int sub = lane & 7, grp = lane >> 3;
     float bs = __int_as_float(0x7f800000);
     int bk = 0x7fffffff;
-    constexpr int NC = 8;
+    constexpr int NC = 4;
 #pragma unroll 1
     for (int kb = k0; kb < k1; kb += 4 * NC) {
         int k[NC];

@@ -471,8 +471,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     tc_fence_after_sync();
     const uint32_t tmem_base = misc->tmem_base;
 
-    // Register budget (640 threads x 96 at launch): control and scan warpgroups hand registers to the update
-    // warpgroups; each role executes its own setmaxnreg first thing (40*128 + 88*256 + 144*256 = 64512).
+    // Register budget: 640 threads x 96 = 61440 registers at launch.  setmaxnreg.inc can only take what
+    // setmaxnreg.dec released inside this CTA, so the totals after rebalancing must not exceed the launch
+    // allocation: 40*128 (control) + 88*256 (scan) + 128*256 (update) = 60416 <= 61440.
     if (warp == 0) {
         reg_dealloc<40>();
         // =========================================================== TMA producer (codebook slices)
@@ -643,7 +644,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             atomicAdd(p.prof + 11, (unsigned long long)t_full);
         }
     } else {
-        reg_alloc<144>();
+        reg_alloc<128>();
         // =========================================================== update warps
         const int u = threadIdx.x - UPD_WARP0 * 32;  // 0..UPD_THREADS-1
         const int sub = u & 7, slot16 = u >> 3;      // 8-lane group per frame
