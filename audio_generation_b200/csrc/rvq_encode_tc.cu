@@ -67,6 +67,8 @@ struct EncParams {
 
 struct __align__(16) Misc {
     uint64_t full[MAX_STAGES_RING], empty[MAX_STAGES_RING], tmem_full[2], tmem_empty[2], a_ready[2], scan_done[2];
+    uint64_t norm_full[2];
+    float norms[2][CHUNK_N];  // scaled ||c||^2 of the chunk in each accumulator buffer (bulk-copied)
     uint32_t tmem_base;
     int dirty_count[2];
     float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
@@ -367,7 +369,7 @@ __device__ __forceinline__ void scan16(const uint32_t (&v)[16], const float* __r
                                        float& m1, float& m2, float& m3, float* dbg) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-        const float4 nn = __ldg(reinterpret_cast<const float4*>(nptr + j));
+        const float4 nn = *reinterpret_cast<const float4*>(nptr + j);  // shared memory, warp-uniform
         const float s0 = fmaf(na, nn.x, __uint_as_float(v[j + 0]));
         const float s1 = fmaf(na, nn.y, __uint_as_float(v[j + 1]));
         const float s2 = fmaf(na, nn.z, __uint_as_float(v[j + 2]));
@@ -456,6 +458,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         for (int i = 0; i < 2; ++i) {
             mbar_init(&misc->tmem_full[i], 1);
             mbar_init(&misc->tmem_empty[i], 4);  // one arrive per scan warp of the group
+            mbar_init(&misc->norm_full[i], 1);
             mbar_init(&misc->a_ready[i], UPD_THREADS);
             mbar_init(&misc->scan_done[i], SCAN_THREADS);
             misc->dirty_count[i] = 0;
@@ -507,6 +510,12 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 const uint32_t buf = g & 1, use = g >> 1;
                 mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
                 tc_fence_after_sync();
+                if (lane == 0) {
+                    // the scan group has released this buffer: its norm slice can be replaced as well
+                    mbar_arrive_expect_tx(&misc->norm_full[buf], CHUNK_N * 4);
+                    bulk_load_1d(misc->norms[buf], p.cb_norm + (size_t)(p.q_begin + job.q) * p.Kpad + c * CHUNK_N,
+                                 CHUNK_N * 4, &misc->norm_full[buf]);
+                }
                 const uint32_t tmem_d = tmem_base + buf * CHUNK_N;
                 for (int ks = 0; ks < n_ks; ++ks, ++it) {
                     const uint32_t s = it % nstage, ph = (it / nstage) & 1;
@@ -546,7 +555,6 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             aphase ^= 1u << sl;
             const float na = misc->row_na[sl][my_row];
             const float delta = misc->row_delta[sl][my_row];
-            const float* nrm_q = p.cb_norm + (size_t)q_abs * p.Kpad;
             Top4 G;
             G.reset();
             long long t1 = clock64();
@@ -555,11 +563,12 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 if ((int)(g & 1) != grp) continue;
                 const long long tw0 = clock64();
                 mbar_wait(&misc->tmem_full[grp], (g >> 1) & 1);
+                mbar_wait(&misc->norm_full[grp], (g >> 1) & 1);
                 tc_fence_after_sync();
                 t_full += clock64() - tw0;
                 float m1 = BIG, m2 = BIG, m3 = BIG;
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CHUNK_N;
-                const float* nptr = nrm_q + c * CHUNK_N;
+                const float* nptr = misc->norms[grp];
                 float* dbg = nullptr;
                 if (kDebug && p.dbg_scores && job.i == 0 && job.q == 0)
                     dbg = p.dbg_scores + (size_t)my_row * p.Kpad + c * CHUNK_N;
