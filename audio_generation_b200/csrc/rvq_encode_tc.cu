@@ -62,7 +62,8 @@ struct EncParams {
     uint32_t off_B, off_misc;  // A tiles (one per slot) at offset 0
     float* dbg_scores;                // [128, Kpad] (bring-up hook) or null
     float* dbg_rowscale;              // [128] or null
-    unsigned long long* prof;         // [8] cycle / event counters (RVQ_PROFILE=1) or null
+    unsigned long long* prof;         // [16] cycle / event counters (RVQ_PROFILE=1) or null
+    int exp;                          // timing experiments (RVQ_EXP, results invalid when != 0)
 };
 
 struct __align__(16) Misc {
@@ -363,10 +364,22 @@ struct Top4 {
     }
 };
 
-// 16 accumulator columns of one frame -> three smallest packed (score | column) values.
-// Two scores at a time: sort the pair, then merge it into the sorted triple (8 FMNMX per pair).
-__device__ __forceinline__ void scan16(const uint32_t (&v)[16], const float* __restrict__ nptr, float na, int col0,
-                                       float& m1, float& m2, float& m3, float* dbg) {
+// sorted triple (m1 <= m2 <= m3) <- three smallest of {m1, m2, m3, a, b}: 8 FMNMX per pair of scores
+__device__ __forceinline__ void merge_pair(float a, float b, float& m1, float& m2, float& m3) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    const float n3 = fminf(fminf(m3, fmaxf(m2, lo)), fmaxf(m1, hi));
+    const float n2 = fminf(fminf(m2, fmaxf(m1, lo)), hi);
+    m1 = fminf(m1, lo);
+    m2 = n2;
+    m3 = n3;
+}
+
+// 16 accumulator columns of one frame -> packed (score | column) values merged into TWO independent sorted
+// triples (A takes columns 0,1,4,5,..., B takes 2,3,6,7,...) so that consecutive merges do not wait on each
+// other.  colpack holds the four column bytes {c+3, c+2, c+1, c} of the first group; one PRMT per score
+// replaces the low mantissa byte by its column.
+__device__ __forceinline__ void scan16(const uint32_t (&v)[16], const float* __restrict__ nptr, float na,
+                                       uint32_t colpack, float (&A)[3], float (&B)[3], float* dbg) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
         const float4 nn = *reinterpret_cast<const float4*>(nptr + j);  // shared memory, warp-uniform
@@ -380,27 +393,13 @@ __device__ __forceinline__ void scan16(const uint32_t (&v)[16], const float* __r
             dbg[j + 2] = s2;
             dbg[j + 3] = s3;
         }
-        // low mantissa byte <- column (one PRMT): the packed value orders by score first, column second
-        const float p0 = __uint_as_float(__byte_perm(__float_as_uint(s0), (uint32_t)(col0 + j + 0), 0x3214));
-        const float p1 = __uint_as_float(__byte_perm(__float_as_uint(s1), (uint32_t)(col0 + j + 1), 0x3214));
-        const float p2 = __uint_as_float(__byte_perm(__float_as_uint(s2), (uint32_t)(col0 + j + 2), 0x3214));
-        const float p3 = __uint_as_float(__byte_perm(__float_as_uint(s3), (uint32_t)(col0 + j + 3), 0x3214));
-        {
-            const float lo = fminf(p0, p1), hi = fmaxf(p0, p1);
-            const float n3 = fminf(fminf(m3, fmaxf(m2, lo)), fmaxf(m1, hi));
-            const float n2 = fminf(fminf(m2, fmaxf(m1, lo)), hi);
-            m1 = fminf(m1, lo);
-            m2 = n2;
-            m3 = n3;
-        }
-        {
-            const float lo = fminf(p2, p3), hi = fmaxf(p2, p3);
-            const float n3 = fminf(fminf(m3, fmaxf(m2, lo)), fmaxf(m1, hi));
-            const float n2 = fminf(fminf(m2, fmaxf(m1, lo)), hi);
-            m1 = fminf(m1, lo);
-            m2 = n2;
-            m3 = n3;
-        }
+        const uint32_t cp = colpack + (uint32_t)j * 0x01010101u;
+        const float p0 = __uint_as_float(__byte_perm(__float_as_uint(s0), cp, 0x3214));
+        const float p1 = __uint_as_float(__byte_perm(__float_as_uint(s1), cp, 0x3215));
+        const float p2 = __uint_as_float(__byte_perm(__float_as_uint(s2), cp, 0x3216));
+        const float p3 = __uint_as_float(__byte_perm(__float_as_uint(s3), cp, 0x3217));
+        merge_pair(p0, p1, A[0], A[1], A[2]);
+        merge_pair(p2, p3, B[0], B[1], B[2]);
     }
 }
 
@@ -566,7 +565,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 mbar_wait(&misc->norm_full[grp], (g >> 1) & 1);
                 tc_fence_after_sync();
                 t_full += clock64() - tw0;
-                float m1 = BIG, m2 = BIG, m3 = BIG;
+                float A[3] = {BIG, BIG, BIG}, B[3] = {BIG, BIG, BIG};
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CHUNK_N;
                 const float* nptr = misc->norms[grp];
                 float* dbg = nullptr;
@@ -576,15 +575,28 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 // the instruction cache (a fully unrolled 256-column body does not)
                 uint32_t va[16], vb[16];
                 tmem_ld_32x16(taddr, va);
+                uint32_t colpack = 0x03020100u;
 #pragma unroll 1
                 for (int cb = 0; cb < CHUNK_N; cb += 32) {
                     tmem_ld_wait();
                     tmem_ld_32x16(taddr + cb + 16, vb);
-                    scan16(va, nptr + cb, na, cb, m1, m2, m3, kDebug && dbg ? dbg + cb : nullptr);
+                    scan16(va, nptr + cb, na, colpack, A, B, kDebug && dbg ? dbg + cb : nullptr);
                     tmem_ld_wait();
                     if (cb + 32 < CHUNK_N) tmem_ld_32x16(taddr + cb + 32, va);
-                    scan16(vb, nptr + cb + 16, na, cb + 16, m1, m2, m3, kDebug && dbg ? dbg + cb + 16 : nullptr);
+                    scan16(vb, nptr + cb + 16, na, colpack + 0x10101010u, A, B,
+                           kDebug && dbg ? dbg + cb + 16 : nullptr);
+                    colpack += 0x20202020u;
                 }
+                // the two triples -> one
+                merge_pair(B[0], B[1], A[0], A[1], A[2]);
+                {
+                    const float n3 = fminf(A[2], fmaxf(A[1], B[2]));
+                    const float n2 = fminf(A[1], fmaxf(A[0], B[2]));
+                    A[0] = fminf(A[0], B[2]);
+                    A[1] = n2;
+                    A[2] = n3;
+                }
+                const float m1 = A[0], m2 = A[1], m3 = A[2];
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&misc->tmem_empty[grp]);
@@ -619,6 +631,11 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 // Codes outside the kept triples score >= hid; hid >= v3 always, and hid >= v4 unless the three
                 // best share one chunk.
                 int nc;
+                if (p.exp) {
+                    G.v1 = 0.f;
+                    G.k1 = my_row;
+                    G.v2 = G.v3 = G.v4 = G.hid = BIG;
+                }
                 const float lim = G.v1 + delta;
                 if (!(G.v1 < BIG) || G.k1 >= Kv || !(lim == lim)) {
                     nc = 4;  // no usable filter result (NaN / overflow): exact scan
@@ -1012,6 +1029,8 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     p.off_misc = sp.off_misc;
     p.dbg_scores = dbg_scores;
     p.dbg_rowscale = dbg_rowscale;
+    static const int exp_mode = getenv("RVQ_EXP") ? atoi(getenv("RVQ_EXP")) : 0;
+    p.exp = exp_mode;
     static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
     if (want_prof && ws && ws_bytes >= 128) {
         // counters live in the LAST 128 bytes of the workspace
