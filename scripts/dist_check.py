@@ -1,0 +1,41 @@
+"""torchrun --nproc-per-node N scripts/dist_check.py : sharded encode + EMA update over N GPUs equals the
+unsharded update on one GPU (replicas bit-identical to each other; vs. single GPU within fp32-atomic tolerance)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from audio_generation_b200 import ResidualQuantizer
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+torch.manual_seed(11)
+nq, K, d, N = 4, 1024, 256, 1 << 16
+m = ResidualQuantizer(nq, d, "ema", K).to(dev).train()
+x = torch.randn(N, d, device=dev)                      # same seed on every rank -> same full batch
+shard = x[rank * N // world:(rank + 1) * N // world]
+for step in range(2):
+    with torch.no_grad():
+        _, idx, commit = m(shard, None, update_codebook=True)
+torch.cuda.synchronize()
+cb = m.codebooks.clone()
+gathered = [torch.empty_like(cb) for _ in range(world)]
+dist.all_gather(gathered, cb)
+identical = all(torch.equal(gathered[0], g) for g in gathered)
+dist.barrier()
+dist.destroy_process_group()                           # single-GPU reference below must not all-reduce
+if rank == 0:
+    torch.manual_seed(11)
+    ref = ResidualQuantizer(nq, d, "ema", K).to(dev).train()
+    for step in range(2):
+        with torch.no_grad():
+            ref(x, None, update_codebook=True)
+    err = (ref.codebooks - cb).abs().max().item()
+    cnt_err = (ref.ema_count - m.ema_count).abs().max().item()
+    print(f"world={world} replicas_bit_identical={identical} max|codebook diff vs single GPU|={err:.3e} "
+          f"max|ema_count diff|={cnt_err:.3e}")
+    assert identical and err < 1e-3 and cnt_err < 1e-3
