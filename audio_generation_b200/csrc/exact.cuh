@@ -119,4 +119,63 @@ __device__ __forceinline__ ScoreIdx exact_scan_warp(const float* __restrict__ r,
     return ScoreIdx{bs, bk};
 }
 
+
+// The same score computed by ONE lane (bit-identical to exact_score8: accumulator j plays lane j of the group,
+// the final sums follow the xor-butterfly order).  r must be readable by every lane (shared memory).
+__device__ __forceinline__ float exact_score_lane(const float* __restrict__ r, const float* __restrict__ c, int d) {
+    float dot[8], nrm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot[j] = nrm[j] = 0.f;
+#pragma unroll 1
+    for (int p = 0; p < d; p += 32) {
+        float4 cv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cv[j] = ldg_nc_v4(c + p + j * 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 rv = *reinterpret_cast<const float4*>(r + p + j * 4);
+            dot[j] = fmaf(rv.x, cv[j].x, dot[j]);
+            dot[j] = fmaf(rv.y, cv[j].y, dot[j]);
+            dot[j] = fmaf(rv.z, cv[j].z, dot[j]);
+            dot[j] = fmaf(rv.w, cv[j].w, dot[j]);
+            nrm[j] = fmaf(cv[j].x, cv[j].x, nrm[j]);
+            nrm[j] = fmaf(cv[j].y, cv[j].y, nrm[j]);
+            nrm[j] = fmaf(cv[j].z, cv[j].z, nrm[j]);
+            nrm[j] = fmaf(cv[j].w, cv[j].w, nrm[j]);
+        }
+    }
+    const float d01 = dot[0] + dot[1], d23 = dot[2] + dot[3], d45 = dot[4] + dot[5], d67 = dot[6] + dot[7];
+    const float n01 = nrm[0] + nrm[1], n23 = nrm[2] + nrm[3], n45 = nrm[4] + nrm[5], n67 = nrm[6] + nrm[7];
+    const float dt = (d01 + d23) + (d45 + d67);
+    const float nt = (n01 + n23) + (n45 + n67);
+    return fmaf(-2.f, dt, nt);
+}
+
+// Exact argmin over codes [k0, k1) for one row by ONE WARP, one code per lane per step (row vector in shared
+// memory).  Every lane returns the warp-wide best.  Same scores, hence same winner, as exact_scan_warp.
+__device__ __forceinline__ ScoreIdx exact_scan_warp_lanes(const float* __restrict__ r_smem,
+                                                          const float* __restrict__ cbq, int d, int k0, int k1,
+                                                          int lane) {
+    float bs = __int_as_float(0x7f800000);
+    int bk = 0x7fffffff;
+#pragma unroll 1
+    for (int k = k0 + lane; k < k1; k += 32) {
+        const float s = exact_score_lane(r_smem, cbq + (size_t)k * d, d);
+        if (better(s, k, bs, bk)) {
+            bs = s;
+            bk = k;
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (better(os, ok, bs, bk)) {
+            bs = os;
+            bk = ok;
+        }
+    }
+    return ScoreIdx{bs, bk};
+}
+
 }  // namespace rvq

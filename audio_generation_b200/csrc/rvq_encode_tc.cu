@@ -81,6 +81,7 @@ struct __align__(16) Misc {
     int mrg_k[3][TILE_M];
     float dirty_s[8];
     int dirty_k[8];
+    alignas(16) float dirty_r[MAX_D];  // residual of the frame being exact-scanned (every lane scores its own code against it)
     double commit_acc[MAX_NQ];
 };
 
@@ -814,7 +815,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 for (int i = 0; i < n_dirty; ++i) {
                     const int row = misc->dirty_rows[sl][i];
                     const int k0 = min(Kv, uwarp * per), k1 = min(Kv, k0 + per);
-                    const ScoreIdx b = exact_scan_warp(rt.at(row, 0), cbq, d, k0, k1, lane);
+                    if (u * 4 < d) *reinterpret_cast<float4*>(&misc->dirty_r[u * 4]) = *reinterpret_cast<float4*>(rt.at(row, u * 4));
+                    named_bar_sync(BAR_UPD, UPD_THREADS);
+                    const ScoreIdx b = exact_scan_warp_lanes(misc->dirty_r, cbq, d, k0, k1, lane);
                     if (lane == 0) {
                         misc->dirty_s[uwarp] = b.s;
                         misc->dirty_k[uwarp] = b.k;

@@ -15,16 +15,20 @@ nq, K, d, N = wl["nq"], wl["K"], wl["d"], min(wl["frames"], 1 << 18)
 q = ResidualQuantizer(nq, d, "ema", K)
 with torch.no_grad():
     q.codebooks.copy_(bench.synth_codebooks(nq, K, d))
-q = q.cuda().eval()
+upd = "--update" in sys.argv
+nsteps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 3
+with torch.no_grad():
+    q.ema_sum.copy_(q.codebooks)
+q = q.cuda().train(upd)
 x = torch.randn(N, d, device="cuda")
-for _ in range(3):
+for _ in range(nsteps):
     with torch.no_grad():
-        q(x)
+        q(x if not upd else torch.randn(N, d, device="cuda"), None, update_codebook=upd)
 torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record()
 with torch.no_grad():
-    q(x)
+    q(x, None, update_codebook=upd)
 ev1.record()
 torch.cuda.synchronize()
 ws = q._ws
@@ -33,7 +37,7 @@ n = max(prof[5], 1)
 ms = ev0.elapsed_time(ev1)
 ctas = min(148, (N + 127) // 128)
 cyc_total = ms * 1e-3 * 1.965e9 * ctas / n
-print(f"workload {name} N={N} ms={ms:.3f} tile-stages={prof[5]}  wall cycles per tile-stage per CTA ~{cyc_total:.0f} "
+print(f"workload {name} update={upd} after {nsteps} steps N={N} ms={ms:.3f} tile-stages={prof[5]}  wall cycles per tile-stage per CTA ~{cyc_total:.0f} "
       f"(MMA floor {K * d * 128 // 4096})")
 print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+wait {prof[1]/n:.0f})  update={prof[2]/n:.0f} "
       f"dirty={prof[3]/n:.0f} (+wait {prof[7]/n:.0f})")
