@@ -75,13 +75,14 @@ struct __align__(16) Misc {
     float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
     int cand[2][3][TILE_M], ncand[2][TILE_M];
     int dirty_rows[2][TILE_M];
+    uint32_t dirty_mask[2][TILE_M];  // per fallback frame: chunks that may hide a candidate
+    uint32_t mrg_mask[TILE_M];
     int score_rows[2][TILE_M];
     int score_count[2];
     float mrg_v[5][TILE_M];
     int mrg_k[3][TILE_M];
     float dirty_s[8];
     int dirty_k[8];
-    alignas(16) float dirty_r[MAX_D];  // residual of the frame being exact-scanned (every lane scores its own code against it)
     double commit_acc[MAX_NQ];
 };
 
@@ -557,6 +558,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             const float delta = misc->row_delta[sl][my_row];
             Top4 G;
             G.reset();
+            uint32_t cmask = 0;  // chunks whose third-best score is within delta of the running best (superset)
             long long t1 = clock64();
             t_wait += t1 - t0;
             for (int c = 0; c < n_chunks; ++c, ++g) {
@@ -608,6 +610,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 G.insert(__uint_as_float(b3 & 0xFFFFFF00u), c * CHUNK_N + (int)(b3 & 0xFFu));
                 // every code of this chunk that is not one of its three best scores at least its third best
                 G.hid = fminf(G.hid, __uint_as_float(b3 & 0xFFFFFF00u));
+                // the running best only improves, so a chunk that is clean against it stays clean
+                if (!(__uint_as_float(b3 & 0xFFFFFF00u) > G.v1 + delta)) cmask |= 1u << (c & 31);
             }
             // ---------------- merge the two groups' candidates, decide how many need an exact score
             if (grp == 1) {
@@ -619,6 +623,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 misc->mrg_k[0][my_row] = G.k1;
                 misc->mrg_k[1][my_row] = G.k2;
                 misc->mrg_k[2][my_row] = G.k3;
+                misc->mrg_mask[my_row] = cmask;
             }
             named_bar_sync(BAR_SCAN, SCAN_THREADS);
             if (grp == 0) {
@@ -656,6 +661,16 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 if (nc == 4) {
                     const int pos = atomicAdd(&misc->dirty_count[sl], 1);
                     misc->dirty_rows[sl][pos] = my_row;
+                    uint32_t mk = cmask | misc->mrg_mask[my_row];
+                    if (n_chunks > 32 || !(G.v1 < BIG) || !(lim == lim)) {
+                        mk = 0xFFFFFFFFu;  // more chunks than mask bits, or no usable filter result: scan everything
+                    } else {
+                        if (G.k1 < Kv) mk |= 1u << (G.k1 / CHUNK_N);
+                        if (G.k2 < Kv) mk |= 1u << (G.k2 / CHUNK_N);
+                        if (G.k3 < Kv) mk |= 1u << (G.k3 / CHUNK_N);
+                    }
+                    const int nch = (Kv + CHUNK_N - 1) / CHUNK_N;
+                    misc->dirty_mask[sl][pos] = nch >= 32 ? mk : (mk & ((1u << nch) - 1u));
                 } else if (nc >= 2) {
                     const int pos = atomicAdd(&misc->score_count[sl], 1);
                     misc->score_rows[sl][pos] = my_row;
@@ -810,14 +825,21 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             const int n_dirty = misc->dirty_count[sl];
             if (n_dirty > 0) {
                 const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
-                const int per = (Kv + UPD_WARPS - 1) / UPD_WARPS;
 #pragma unroll 1
                 for (int i = 0; i < n_dirty; ++i) {
                     const int row = misc->dirty_rows[sl][i];
-                    const int k0 = min(Kv, uwarp * per), k1 = min(Kv, k0 + per);
-                    if (u * 4 < d) *reinterpret_cast<float4*>(&misc->dirty_r[u * 4]) = *reinterpret_cast<float4*>(rt.at(row, u * 4));
-                    named_bar_sync(BAR_UPD, UPD_THREADS);
-                    const ScoreIdx b = exact_scan_warp_lanes(misc->dirty_r, cbq, d, k0, k1, lane);
+                    // only chunks whose third-best score could be inside the margin can hide a candidate
+                    // (plus the chunks of the three kept candidates, which the scan marked as well)
+                    const uint32_t cmask = misc->dirty_mask[sl][i];
+                    ScoreIdx b{__int_as_float(0x7f800000), 0x7fffffff};
+                    for (uint32_t mm = cmask; mm; mm &= mm - 1) {
+                        const int cbeg = (__ffs(mm) - 1) * CHUNK_N;
+                        const int cend = min(Kv, cbeg + CHUNK_N);
+                        const int per_c = (CHUNK_N + UPD_WARPS - 1) / UPD_WARPS;
+                        const int k0 = min(cend, cbeg + uwarp * per_c), k1 = min(cend, k0 + per_c);
+                        const ScoreIdx bc = exact_scan_warp(rt.at(row, 0), cbq, d, k0, k1, lane);
+                        if (better(bc.s, bc.k, b.s, b.k)) b = bc;
+                    }
                     if (lane == 0) {
                         misc->dirty_s[uwarp] = b.s;
                         misc->dirty_k[uwarp] = b.k;
@@ -974,6 +996,10 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
                   const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
                   float* stats_cnt, void* ws, size_t ws_bytes, float* dbg_scores, float* dbg_rowscale,
                   cudaStream_t st) {
+    if (K > 32 * CHUNK_N) {
+        set_error("rvq_encode: at most %d codes per stage are supported (got %d)", 32 * CHUNK_N, K);
+        return RVQ_ERR_ARG;
+    }
     if (nq > MAX_NQ) {
         set_error("rvq_encode: at most %d stages are supported (got %d)", MAX_NQ, nq);
         return RVQ_ERR_ARG;
