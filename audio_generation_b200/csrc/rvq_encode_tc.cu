@@ -64,6 +64,7 @@ struct EncParams {
     float* dbg_rowscale;              // [128] or null
     unsigned long long* prof;         // [16] cycle / event counters (RVQ_PROFILE=1) or null
     int exp;                          // timing experiments (RVQ_EXP, results invalid when != 0)
+    int one;                          // the constant 1, opaque to the compiler (see merge_pair)
 };
 
 struct __align__(16) Misc {
@@ -220,6 +221,7 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
 // Batched form of apply_row for d = 128 * SEGS: RB frames per 8-lane group with every load of the batch
 // issued before the first dependent instruction (one L2 round trip per batch instead of one per frame).
 // Inactive frames (exact-scan fallback pending) load harmlessly and store nothing.
+// The bound on max|r'| that picks the next operand scale is ||r||_2 + max|c| (no per-element max needed).
 template <int RB, int SEGS>
 __device__ __forceinline__ void apply_rows(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
                                            const int* rows, const bool* active, const bool* row_valid,
@@ -236,16 +238,19 @@ __device__ __forceinline__ void apply_rows(const EncParams& p, Misc* misc, uint8
         cmax_q = p.cb_meta[(size_t)q_abs * META_STRIDE + 2];
     }
     float4 rv[RB][SEGS * 4], cv[RB][SEGS * 4];
-    const float* cw[RB];
+    float* rrow[RB];
 #pragma unroll
     for (int j = 0; j < RB; ++j) {
-        cw[j] = p.cb + ((size_t)q_abs * p.K + kwin[j]) * d;
+        rrow[j] = rt.at(rows[j], sub * 4);
+        const float* cw = p.cb + ((size_t)q_abs * p.K + kwin[j]) * d + sub * 4;
 #pragma unroll
         for (int i = 0; i < SEGS * 4; ++i) {
-            rv[j][i] = *reinterpret_cast<float4*>(rt.at(rows[j], sub * 4 + i * 32));
-            cv[j][i] = ldg_nc_v4(cw[j] + sub * 4 + i * 32);
+            rv[j][i] = *reinterpret_cast<float4*>(rrow[j] + i * 32);
+            cv[j][i] = ldg_nc_v4(cw + i * 32);
         }
     }
+    // A-tile address pieces: feature c = sub*4 + i*32 -> slice i>>1, 16-byte chunk (sub>>1) + (i&1)*4 (xor row&7)
+    const uint32_t s1 = (uint32_t)sub >> 1, s0 = ((uint32_t)sub & 1u) << 3;
 #pragma unroll
     for (int j = 0; j < RB; ++j) {
         int a = 0;
@@ -255,36 +260,42 @@ __device__ __forceinline__ void apply_rows(const EncParams& p, Misc* misc, uint8
             a = pick_row_exp(misc->row_amax[sl][rows[j]] + cmax_q, b, force_exact);
             sa = exp2i(a);
         }
-        float sq = 0.f, amax = 0.f;
-        float* ssum = (p.stats_sum && row_valid[j] && active[j]) ? p.stats_sum + ((size_t)q_abs * p.K + kwin[j]) * d
-                                                                 : nullptr;
+        float sq = 0.f;
+        float* ssum = (p.stats_sum && row_valid[j] && active[j])
+                          ? p.stats_sum + ((size_t)q_abs * p.K + kwin[j]) * d + sub * 4
+                          : nullptr;
+        uint8_t* arow = smem_a + (uint32_t)rows[j] * 128u + s0;
+        const uint32_t rx = (uint32_t)rows[j] & 7u;
 #pragma unroll
         for (int i = 0; i < SEGS * 4; ++i) {
-            const int c = sub * 4 + i * 32;
-            if (ssum) red_add_v4(ssum + c, rv[j][i]);
+            if (ssum) red_add_v4(ssum + i * 32, rv[j][i]);
             float4 nr;
             nr.x = rv[j][i].x - cv[j][i].x;
             nr.y = rv[j][i].y - cv[j][i].y;
             nr.z = rv[j][i].z - cv[j][i].z;
             nr.w = rv[j][i].w - cv[j][i].w;
-            if (active[j]) {
-                *reinterpret_cast<float4*>(rt.at(rows[j], c)) = nr;
-                if (write_a) store_a4(smem_a, rows[j], c, nr, sa);
-            }
             sq = fmaf(nr.x, nr.x, sq);
             sq = fmaf(nr.y, nr.y, sq);
             sq = fmaf(nr.z, nr.z, sq);
             sq = fmaf(nr.w, nr.w, sq);
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(nr.x), fabsf(nr.y)), fmaxf(fabsf(nr.z), fabsf(nr.w))));
+            if (active[j]) {
+                *reinterpret_cast<float4*>(rrow[j] + i * 32) = nr;
+                if (write_a) {
+                    const __half2 h01 = __floats2half2_rn(nr.x * sa, nr.y * sa);
+                    const __half2 h23 = __floats2half2_rn(nr.z * sa, nr.w * sa);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+                    *reinterpret_cast<uint2*>(arow + (uint32_t)(i >> 1) * A_SLICE_BYTES +
+                                              (((s1 + (uint32_t)(i & 1) * 4u) ^ rx) << 4)) = pk;
+                }
+            }
         }
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        }
+        for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         sq_out[j] = sq;
         if (active[j] && sub == 0) {
-            misc->row_amax[sl][rows[j]] = amax;
+            misc->row_amax[sl][rows[j]] = sqrtf(sq) * 1.00002f;   // ||r'||_2 >= max|r'|
             if (write_a) {
                 if (!isfinite(sq)) force_exact = true;
                 write_row_consts(p, misc, sl, rows[j], d, sq, force_exact, a, b, sb, cnmax);
@@ -367,8 +378,13 @@ struct Top4 {
 };
 
 // sorted triple (m1 <= m2 <= m3) <- three smallest of {m1, m2, m3, a, b}: 8 FMNMX per pair of scores
-__device__ __forceinline__ void merge_pair(float a, float b, float& m1, float& m2, float& m3) {
-    const float lo = fminf(a, b), hi = fmaxf(a, b);
+// `one` is the runtime constant 1 (kernel parameter): hi = a + b - lo is computed on the bit patterns with two
+// IMADs (FMA pipe) instead of one more FMNMX on the ALU pipe, which is the pipe that bounds the epilogue; a
+// literal 1 would let ptxas turn them back into ALU-pipe IADD3s.
+__device__ __forceinline__ void merge_pair(float a, float b, float& m1, float& m2, float& m3, int one) {
+    const float lo = fminf(a, b);
+    const int t_ = __float_as_int(a) * one + __float_as_int(b);
+    const float hi = __int_as_float(t_ - __float_as_int(lo) * one);
     const float n3 = fminf(fminf(m3, fmaxf(m2, lo)), fmaxf(m1, hi));
     const float n2 = fminf(fminf(m2, fmaxf(m1, lo)), hi);
     m1 = fminf(m1, lo);
@@ -381,7 +397,7 @@ __device__ __forceinline__ void merge_pair(float a, float b, float& m1, float& m
 // other.  colpack holds the four column bytes {c+3, c+2, c+1, c} of the first group; one PRMT per score
 // replaces the low mantissa byte by its column.
 __device__ __forceinline__ void scan16(const uint32_t (&v)[16], const float* __restrict__ nptr, float na,
-                                       uint32_t colpack, float (&A)[3], float (&B)[3], float* dbg) {
+                                       uint32_t colpack, float (&A)[3], float (&B)[3], float* dbg, int one) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
         const float4 nn = *reinterpret_cast<const float4*>(nptr + j);  // shared memory, warp-uniform
@@ -400,8 +416,8 @@ __device__ __forceinline__ void scan16(const uint32_t (&v)[16], const float* __r
         const float p1 = __uint_as_float(__byte_perm(__float_as_uint(s1), cp, 0x3215));
         const float p2 = __uint_as_float(__byte_perm(__float_as_uint(s2), cp, 0x3216));
         const float p3 = __uint_as_float(__byte_perm(__float_as_uint(s3), cp, 0x3217));
-        merge_pair(p0, p1, A[0], A[1], A[2]);
-        merge_pair(p2, p3, B[0], B[1], B[2]);
+        merge_pair(p0, p1, A[0], A[1], A[2], one);
+        merge_pair(p2, p3, B[0], B[1], B[2], one);
     }
 }
 
@@ -547,6 +563,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         const int grp = e >> 7;                       // scan group = accumulator buffer
         const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
         uint32_t g = 0, aphase = 0;
+        const int one = p.one;
         long long t_scan = 0, t_wait = 0, t_full = 0;
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
             const int sl = job.slot % nslots;
@@ -583,15 +600,15 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 for (int cb = 0; cb < CHUNK_N; cb += 32) {
                     tmem_ld_wait();
                     tmem_ld_32x16(taddr + cb + 16, vb);
-                    scan16(va, nptr + cb, na, colpack, A, B, kDebug && dbg ? dbg + cb : nullptr);
+                    scan16(va, nptr + cb, na, colpack, A, B, kDebug && dbg ? dbg + cb : nullptr, one);
                     tmem_ld_wait();
                     if (cb + 32 < CHUNK_N) tmem_ld_32x16(taddr + cb + 32, va);
                     scan16(vb, nptr + cb + 16, na, colpack + 0x10101010u, A, B,
-                           kDebug && dbg ? dbg + cb + 16 : nullptr);
+                           kDebug && dbg ? dbg + cb + 16 : nullptr, one);
                     colpack += 0x20202020u;
                 }
                 // the two triples -> one
-                merge_pair(B[0], B[1], A[0], A[1], A[2]);
+                merge_pair(B[0], B[1], A[0], A[1], A[2], one);
                 {
                     const float n3 = fminf(A[2], fmaxf(A[1], B[2]));
                     const float n2 = fminf(A[1], fmaxf(A[0], B[2]));
@@ -1060,6 +1077,7 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     p.dbg_rowscale = dbg_rowscale;
     static const int exp_mode = getenv("RVQ_EXP") ? atoi(getenv("RVQ_EXP")) : 0;
     p.exp = exp_mode;
+    p.one = 1;
     static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
     if (want_prof && ws && ws_bytes >= 128) {
         // counters live in the LAST 128 bytes of the workspace
