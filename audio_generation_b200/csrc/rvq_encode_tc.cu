@@ -304,6 +304,64 @@ __device__ __forceinline__ void apply_rows(const EncParams& p, Misc* misc, uint8
     }
 }
 
+// One frame with NP float4 pieces per lane (d = 32*NP), all loads of the frame in flight together.
+// Scalar-argument twin of apply_rows<1, NP/4> (kept separate: simpler code for the compiler).
+template <int NP>
+__device__ __forceinline__ void apply_row_fixed(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt,
+                                                int sl, int row, bool active, bool row_valid, int kwin, int q_abs,
+                                                int next_q_abs, int sub, float* sq_out) {
+    constexpr int d = 32 * NP;
+    const bool write_a = next_q_abs >= 0;
+    float sb = 1.f, cnmax = 0.f, sa = 0.f;
+    int a = 0, b = 0;
+    bool force_exact = false;
+    if (write_a) {
+        const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
+        sb = mq[0];
+        cnmax = mq[1];
+        b = ilog2f_floor(sb);
+        a = pick_row_exp(misc->row_amax[sl][row] + p.cb_meta[(size_t)q_abs * META_STRIDE + 2], b, force_exact);
+        sa = exp2i(a);
+    }
+    float* rrow = rt.at(row, sub * 4);
+    const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d + sub * 4;
+    float4 rv[NP], cv[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) rv[i] = *reinterpret_cast<const float4*>(rrow + i * 32);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) cv[i] = ldg_nc_v4(cw + i * 32);
+    float* ssum = (p.stats_sum && row_valid && active) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d + sub * 4
+                                                       : nullptr;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        if (ssum) red_add_v4(ssum + i * 32, rv[i]);
+        float4 nr;
+        nr.x = rv[i].x - cv[i].x;
+        nr.y = rv[i].y - cv[i].y;
+        nr.z = rv[i].z - cv[i].z;
+        nr.w = rv[i].w - cv[i].w;
+        sq = fmaf(nr.x, nr.x, sq);
+        sq = fmaf(nr.y, nr.y, sq);
+        sq = fmaf(nr.z, nr.z, sq);
+        sq = fmaf(nr.w, nr.w, sq);
+        if (active) {
+            *reinterpret_cast<float4*>(rrow + i * 32) = nr;
+            if (write_a) store_a4(smem_a, row, sub * 4 + i * 32, nr, sa);
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    *sq_out = sq;
+    if (active && sub == 0) {
+        misc->row_amax[sl][row] = sqrtf(sq) * 1.00002f;
+        if (write_a) {
+            if (!isfinite(sq)) force_exact = true;
+            write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
+        }
+    }
+}
+
 // Stage-0 initialisation of one frame by an 8-lane group: x -> residual scratch, exact max -> operand scale,
 // fp16 operand row and row constants of the first stage (two passes: the scale needs the row maximum).
 __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
@@ -799,9 +857,19 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
             };
-            if (d == 128 || d == 256) {
+            if (d == 256) {
+#pragma unroll 1
+                for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
+                    const bool active = misc->ncand[sl][row] != 4;
+                    const int kwin = active ? misc->cand[sl][0][row] : 0;
+                    float sq;
+                    apply_row_fixed<8>(p, misc, a_tile, rt, sl, row, active, n0 + row < p.N, kwin, q_abs, next_q_abs,
+                                       sub, &sq);
+                    post_row(row, active, kwin, sq);
+                }
+            } else if (d == 128) {
                 constexpr int RB_MAX = 2;
-                const int rb = d == 128 ? 2 : 1;
+                const int rb = 2;
 #pragma unroll 1
                 for (int r0 = slot16; r0 < TILE_M; r0 += ROWS_PER_PASS * rb) {
                     int rows[RB_MAX], kwin[RB_MAX];
@@ -814,10 +882,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         kwin[j] = active[j] ? misc->cand[sl][0][rows[j]] : 0;
                         valid[j] = n0 + rows[j] < p.N;
                     }
-                    if (d == 128)
-                        apply_rows<2, 1>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
-                    else
-                        apply_rows<1, 2>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
+                    apply_rows<2, 1>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
 #pragma unroll
                     for (int j = 0; j < RB_MAX; ++j)
                         if (j < rb) post_row(rows[j], active[j], kwin[j], sq[j]);
