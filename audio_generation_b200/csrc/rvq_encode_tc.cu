@@ -218,15 +218,14 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
     }
 }
 
-// Batched form of apply_row for d = 128 * SEGS: RB frames per 8-lane group with every load of the batch
-// issued before the first dependent instruction (one L2 round trip per batch instead of one per frame).
-// Inactive frames (exact-scan fallback pending) load harmlessly and store nothing.
-// The bound on max|r'| that picks the next operand scale is ||r||_2 + max|c| (no per-element max needed).
-template <int RB, int SEGS>
-__device__ __forceinline__ void apply_rows(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
-                                           const int* rows, const bool* active, const bool* row_valid,
-                                           const int* kwin, int q_abs, int next_q_abs, int sub, float* sq_out) {
-    constexpr int d = 128 * SEGS;
+// Two frames of d = 128 per 8-lane group with every load of both frames issued before the first dependent
+// instruction (one L2 round trip per pair of frames).  Inactive frames (exact-scan fallback pending) load
+// harmlessly and store nothing.  The bound on max|r'| that picks the next operand scale is ||r||_2 + max|c|.
+__device__ __forceinline__ void apply_two_rows_128(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt,
+                                                   int sl, int row0, int row1, bool act0, bool act1, bool val0,
+                                                   bool val1, int kw0, int kw1, int q_abs, int next_q_abs, int sub,
+                                                   float& sq0_out, float& sq1_out) {
+    constexpr int d = 128;
     const bool write_a = next_q_abs >= 0;
     float sb = 1.f, cnmax = 0.f, cmax_q = 0.f;
     int b = 0;
@@ -237,49 +236,56 @@ __device__ __forceinline__ void apply_rows(const EncParams& p, Misc* misc, uint8
         b = ilog2f_floor(sb);
         cmax_q = p.cb_meta[(size_t)q_abs * META_STRIDE + 2];
     }
-    float4 rv[RB][SEGS * 4], cv[RB][SEGS * 4];
-    float* rrow[RB];
+    float* rr0 = rt.at(row0, sub * 4);
+    float* rr1 = rt.at(row1, sub * 4);
+    const float* cw0 = p.cb + ((size_t)q_abs * p.K + kw0) * d + sub * 4;
+    const float* cw1 = p.cb + ((size_t)q_abs * p.K + kw1) * d + sub * 4;
+    float4 r0[4], r1[4], c0[4], c1[4];
 #pragma unroll
-    for (int j = 0; j < RB; ++j) {
-        rrow[j] = rt.at(rows[j], sub * 4);
-        const float* cw = p.cb + ((size_t)q_abs * p.K + kwin[j]) * d + sub * 4;
+    for (int i = 0; i < 4; ++i) r0[i] = *reinterpret_cast<const float4*>(rr0 + i * 32);
 #pragma unroll
-        for (int i = 0; i < SEGS * 4; ++i) {
-            rv[j][i] = *reinterpret_cast<float4*>(rrow[j] + i * 32);
-            cv[j][i] = ldg_nc_v4(cw + i * 32);
-        }
-    }
+    for (int i = 0; i < 4; ++i) r1[i] = *reinterpret_cast<const float4*>(rr1 + i * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c0[i] = ldg_nc_v4(cw0 + i * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c1[i] = ldg_nc_v4(cw1 + i * 32);
     // A-tile address pieces: feature c = sub*4 + i*32 -> slice i>>1, 16-byte chunk (sub>>1) + (i&1)*4 (xor row&7)
     const uint32_t s1 = (uint32_t)sub >> 1, s0 = ((uint32_t)sub & 1u) << 3;
 #pragma unroll
-    for (int j = 0; j < RB; ++j) {
+    for (int j = 0; j < 2; ++j) {
+        const int row = j ? row1 : row0;
+        const bool active = j ? act1 : act0;
+        const bool valid = j ? val1 : val0;
+        const int kwin = j ? kw1 : kw0;
+        float* rrow = j ? rr1 : rr0;
         int a = 0;
         float sa = 0.f;
         bool force_exact = false;
         if (write_a) {
-            a = pick_row_exp(misc->row_amax[sl][rows[j]] + cmax_q, b, force_exact);
+            a = pick_row_exp(misc->row_amax[sl][row] + cmax_q, b, force_exact);
             sa = exp2i(a);
         }
         float sq = 0.f;
-        float* ssum = (p.stats_sum && row_valid[j] && active[j])
-                          ? p.stats_sum + ((size_t)q_abs * p.K + kwin[j]) * d + sub * 4
-                          : nullptr;
-        uint8_t* arow = smem_a + (uint32_t)rows[j] * 128u + s0;
-        const uint32_t rx = (uint32_t)rows[j] & 7u;
+        float* ssum = (p.stats_sum && valid && active) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d + sub * 4
+                                                       : nullptr;
+        uint8_t* arow = smem_a + (uint32_t)row * 128u + s0;
+        const uint32_t rx = (uint32_t)row & 7u;
 #pragma unroll
-        for (int i = 0; i < SEGS * 4; ++i) {
-            if (ssum) red_add_v4(ssum + i * 32, rv[j][i]);
+        for (int i = 0; i < 4; ++i) {
+            const float4 rv = j ? r1[i] : r0[i];
+            const float4 cv = j ? c1[i] : c0[i];
+            if (ssum) red_add_v4(ssum + i * 32, rv);
             float4 nr;
-            nr.x = rv[j][i].x - cv[j][i].x;
-            nr.y = rv[j][i].y - cv[j][i].y;
-            nr.z = rv[j][i].z - cv[j][i].z;
-            nr.w = rv[j][i].w - cv[j][i].w;
+            nr.x = rv.x - cv.x;
+            nr.y = rv.y - cv.y;
+            nr.z = rv.z - cv.z;
+            nr.w = rv.w - cv.w;
             sq = fmaf(nr.x, nr.x, sq);
             sq = fmaf(nr.y, nr.y, sq);
             sq = fmaf(nr.z, nr.z, sq);
             sq = fmaf(nr.w, nr.w, sq);
-            if (active[j]) {
-                *reinterpret_cast<float4*>(rrow[j] + i * 32) = nr;
+            if (active) {
+                *reinterpret_cast<float4*>(rrow + i * 32) = nr;
                 if (write_a) {
                     const __half2 h01 = __floats2half2_rn(nr.x * sa, nr.y * sa);
                     const __half2 h23 = __floats2half2_rn(nr.z * sa, nr.w * sa);
@@ -293,12 +299,12 @@ __device__ __forceinline__ void apply_rows(const EncParams& p, Misc* misc, uint8
         }
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        sq_out[j] = sq;
-        if (active[j] && sub == 0) {
-            misc->row_amax[sl][rows[j]] = sqrtf(sq) * 1.00002f;   // ||r'||_2 >= max|r'|
+        if (j) sq1_out = sq; else sq0_out = sq;
+        if (active && sub == 0) {
+            misc->row_amax[sl][row] = sqrtf(sq) * 1.00002f;   // ||r'||_2 >= max|r'|
             if (write_a) {
                 if (!isfinite(sq)) force_exact = true;
-                write_row_consts(p, misc, sl, rows[j], d, sq, force_exact, a, b, sb, cnmax);
+                write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
             }
         }
     }
@@ -823,7 +829,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             // ---------------- exact re-rank of the frames with 2 or 3 candidates (compacted list)
             const long long ts0 = clock64();
             const int n_score = misc->score_count[sl];
-            for (int base = 0; base < n_score; base += ROWS_PER_PASS) {
+            for (int base = 0; base < (p.exp == 4 ? 0 : n_score); base += ROWS_PER_PASS) {
                 const int i = base + slot16;
                 const bool sc = i < n_score;
                 const int row = misc->score_rows[sl][sc ? i : 0];
@@ -857,7 +863,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
             };
-            if (d == 256) {
+            if (p.exp == 4) {
+            } else if (d == 256) {
 #pragma unroll 1
                 for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                     const bool active = misc->ncand[sl][row] != 4;
@@ -868,24 +875,16 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                     post_row(row, active, kwin, sq);
                 }
             } else if (d == 128) {
-                constexpr int RB_MAX = 2;
-                const int rb = 2;
 #pragma unroll 1
-                for (int r0 = slot16; r0 < TILE_M; r0 += ROWS_PER_PASS * rb) {
-                    int rows[RB_MAX], kwin[RB_MAX];
-                    bool active[RB_MAX], valid[RB_MAX];
-                    float sq[RB_MAX];
-#pragma unroll
-                    for (int j = 0; j < RB_MAX; ++j) {
-                        rows[j] = r0 + (j < rb ? j : 0) * ROWS_PER_PASS;
-                        active[j] = misc->ncand[sl][rows[j]] != 4;
-                        kwin[j] = active[j] ? misc->cand[sl][0][rows[j]] : 0;
-                        valid[j] = n0 + rows[j] < p.N;
-                    }
-                    apply_rows<2, 1>(p, misc, a_tile, rt, sl, rows, active, valid, kwin, q_abs, next_q_abs, sub, sq);
-#pragma unroll
-                    for (int j = 0; j < RB_MAX; ++j)
-                        if (j < rb) post_row(rows[j], active[j], kwin[j], sq[j]);
+                for (int r0 = slot16; r0 < TILE_M; r0 += 2 * ROWS_PER_PASS) {
+                    const int r1 = r0 + ROWS_PER_PASS;
+                    const bool a0 = misc->ncand[sl][r0] != 4, a1 = misc->ncand[sl][r1] != 4;
+                    const int k0 = a0 ? misc->cand[sl][0][r0] : 0, k1 = a1 ? misc->cand[sl][0][r1] : 0;
+                    float sq0, sq1;
+                    apply_two_rows_128(p, misc, a_tile, rt, sl, r0, r1, a0, a1, n0 + r0 < p.N, n0 + r1 < p.N, k0, k1,
+                                       q_abs, next_q_abs, sub, sq0, sq1);
+                    post_row(r0, a0, k0, sq0);
+                    post_row(r1, a1, k1, sq1);
                 }
             } else {
 #pragma unroll 1
