@@ -1053,8 +1053,9 @@ SmemPlan plan_smem(int d, int smem_max) {
     SmemPlan s{};
     const uint32_t a_bytes = (uint32_t)(d / KSLICE) * A_SLICE_BYTES;
     const uint32_t misc_bytes = (uint32_t)((sizeof(Misc) + 1023) / 1024 * 1024);
-    // two tiles in flight (ping-pong between scan and update warps) if >= 3 ring stages still fit
-    s.nslots = (2 * a_bytes + misc_bytes + 3 * B_STAGE_BYTES + 1024 <= (uint32_t)smem_max) ? 2 : 1;
+    // two tiles in flight (ping-pong between scan and update warps) if >= 2 ring stages still fit: the epilogue,
+    // not the MMA, is the long pole, so a shallow codebook ring costs less than serialising scan and update
+    s.nslots = (2 * a_bytes + misc_bytes + 2 * B_STAGE_BYTES + 1024 <= (uint32_t)smem_max) ? 2 : 1;
     s.off_B = (uint32_t)s.nslots * a_bytes;
     const uint32_t fixed = s.off_B + misc_bytes + 1024;
     int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / B_STAGE_BYTES) : 0;
