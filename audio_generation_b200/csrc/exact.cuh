@@ -25,7 +25,7 @@ __device__ __forceinline__ bool better(float s, int k, float bs, int bk) {
 
 // One segment of NP float4 pieces per lane (NP*32 features) starting at feature p0 (lane offset included).
 template <int NC, int NP>
-__device__ __forceinline__ void exact_seg(const float* __restrict__ r, const float* const* c, int p0, float* dot,
+__device__ __forceinline__ void exact_seg(const float* r, const float* const* c, int p0, float* dot,
                                           float* nrm) {
     float4 rv[NP], cv[NC][NP];
 #pragma unroll
@@ -53,7 +53,7 @@ __device__ __forceinline__ void exact_seg(const float* __restrict__ r, const flo
 // r: row vector (generic pointer: shared or global), c[j]: code vectors (global). d % 64 == 0.
 // All 8 lanes of the group obtain the same out[j].
 template <int NC>
-__device__ __forceinline__ void exact_score8_n(const float* __restrict__ r, const float* const* c, int d, int sub,
+__device__ __forceinline__ void exact_score8_n(const float* r, const float* const* c, int d, int sub,
                                                float* out) {
     float dot[NC], nrm[NC];
 #pragma unroll
@@ -73,7 +73,7 @@ __device__ __forceinline__ void exact_score8_n(const float* __restrict__ r, cons
     }
 }
 
-__device__ __forceinline__ float exact_score8(const float* __restrict__ r, const float* __restrict__ c, int d,
+__device__ __forceinline__ float exact_score8(const float* r, const float* __restrict__ c, int d,
                                               int sub) {
     const float* const cc[1] = {c};
     float o[1];
@@ -83,7 +83,7 @@ __device__ __forceinline__ float exact_score8(const float* __restrict__ r, const
 
 // Exact argmin over codes [k0, k1) for one row by ONE WARP: 4 groups of 8 lanes, 4 codes per group per step
 // (16 codes per warp step, all loads of a step in flight together).  Every lane returns the warp-wide best.
-__device__ __forceinline__ ScoreIdx exact_scan_warp(const float* __restrict__ r, const float* __restrict__ cbq,
+__device__ __forceinline__ ScoreIdx exact_scan_warp(const float* r, const float* __restrict__ cbq,
                                                     int d, int k0, int k1, int lane) {
     const int sub = lane & 7, grp = lane >> 3;
     float bs = __int_as_float(0x7f800000);
@@ -122,7 +122,7 @@ __device__ __forceinline__ ScoreIdx exact_scan_warp(const float* __restrict__ r,
 
 // The same score computed by ONE lane (bit-identical to exact_score8: accumulator j plays lane j of the group,
 // the final sums follow the xor-butterfly order).  r must be readable by every lane (shared memory).
-__device__ __forceinline__ float exact_score_lane(const float* __restrict__ r, const float* __restrict__ c, int d) {
+__device__ __forceinline__ float exact_score_lane(const float* r, const float* __restrict__ c, int d) {
     float dot[8], nrm[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) dot[j] = nrm[j] = 0.f;
@@ -153,7 +153,7 @@ __device__ __forceinline__ float exact_score_lane(const float* __restrict__ r, c
 
 // Exact argmin over codes [k0, k1) for one row by ONE WARP, one code per lane per step (row vector in shared
 // memory).  Every lane returns the warp-wide best.  Same scores, hence same winner, as exact_scan_warp.
-__device__ __forceinline__ ScoreIdx exact_scan_warp_lanes(const float* __restrict__ r_smem,
+__device__ __forceinline__ ScoreIdx exact_scan_warp_lanes(const float* r_smem,
                                                           const float* __restrict__ cbq, int d, int k0, int k1,
                                                           int lane) {
     float bs = __int_as_float(0x7f800000);
