@@ -281,3 +281,39 @@ def test_refuses_cpu_tensor():
     m = make(2, 256, 64)
     with pytest.raises(RVQError):
         m(torch.randn(10, 64))
+
+
+def test_filter_scores_match_fp16_reference():
+    """Bring-up hook: the tensor-core filter alone (TMA -> tcgen05 -> TMEM -> epilogue add) reproduces
+    (2^a r)_fp16 . (-2 2^b C)_fp16^T + 2^(a-b) * 2^(2b)||c||^2 to fp32 accumulation accuracy."""
+    import ctypes as C
+    from audio_generation_b200 import _lib
+    from audio_generation_b200.quantizer import _ptr, _stream
+    lib = _lib.load()
+    for (K, d) in [(1024, 128), (512, 256), (300, 512), (256, 64)]:
+        m = make(2, K, d)
+        op, nrm, meta = m._prepared()
+        Kpad = (K + 255) // 256 * 256
+        x = torch.randn(128, d, device="cuda") * 3.0
+        scores = torch.full((128, Kpad), float("nan"), device="cuda")
+        rs = torch.zeros(128, device="cuda")
+        _lib.check(lib.rvq_debug_stage_scores(_ptr(x), d, K, 1, _ptr(op), _ptr(nrm), _ptr(meta), _ptr(scores), _ptr(rs),
+                                              _stream()), "rvq_debug_stage_scores")
+        torch.cuda.synchronize()
+        sb = meta.reshape(2, 8)[1, 0]
+        a_h = (x * rs[:, None]).half().double()
+        b_h = op.reshape(2, Kpad, d)[1].double()
+        ref = a_h @ b_h.t() + ((rs / sb)[:, None] * nrm.reshape(2, Kpad)[1][None, :]).double()
+        err = (scores.double() - ref).abs()[:, :K].max()
+        assert not torch.isnan(scores[:, :K]).any()
+        assert err <= 2e-6 * ref[:, :K].abs().max(), (K, d, float(err))
+        assert (scores[:, :K].argmin(1) == ref[:, :K].argmin(1)).float().mean() > 0.99
+
+
+def test_unsupported_shapes_are_refused():
+    from audio_generation_b200 import ResidualQuantizer
+    from audio_generation_b200._lib import RVQError
+    with pytest.raises(RVQError):
+        ResidualQuantizer(2, 100, "ema", 64).cuda()(torch.randn(8, 100, device="cuda"))       # d % 64 != 0
+    with pytest.raises(RVQError):
+        ResidualQuantizer(1, 64, "ema", 8448).cuda()(torch.randn(8, 64, device="cuda"))       # K > 8192
