@@ -120,6 +120,50 @@ __device__ __forceinline__ ScoreIdx exact_scan_warp(const float* r, const float*
 }
 
 
+// Exact argmin by ONE WARP over the codes {16 * it + j : it0 <= it < it1, bit j of cols set, code < Kv}
+// (4 groups of 8 lanes, 4 codes per group per step).  Every lane returns the warp-wide best.
+__device__ __forceinline__ ScoreIdx exact_scan_cols(const float* r, const float* __restrict__ cbq, int d, int it0,
+                                                    int it1, uint32_t cols, int Kv, int lane) {
+    const int sub = lane & 7, grp = lane >> 3;
+    float bs = __int_as_float(0x7f800000);
+    int bk = 0x7fffffff;
+    constexpr int NC = 4;
+    const int pc = __popc(cols);
+    const int total = (it1 - it0) * pc;
+#pragma unroll 1
+    for (int eb = 0; eb < total; eb += 4 * NC) {
+        int k[NC];
+        const float* cc[NC];
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const int e = eb + j * 4 + grp;
+            const int ec = e < total ? e : 0;
+            const int a = ec / pc, jj = ec - a * pc;
+            const int kk = (it0 + a) * 16 + (int)__fns(cols, 0, jj + 1);
+            k[j] = (e < total && kk < Kv) ? kk : -1;
+            cc[j] = cbq + (size_t)(k[j] >= 0 ? k[j] : 0) * d;
+        }
+        float s[NC];
+        exact_score8_n<NC>(r, cc, d, sub, s);
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+            if (k[j] >= 0 && better(s[j], k[j], bs, bk)) {
+                bs = s[j];
+                bk = k[j];
+            }
+    }
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+        const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        if (better(os, ok, bs, bk)) {
+            bs = os;
+            bk = ok;
+        }
+    }
+    return ScoreIdx{bs, bk};
+}
+
 // The same score computed by ONE lane (bit-identical to exact_score8: accumulator j plays lane j of the group,
 // the final sums follow the xor-butterfly order).  r must be readable by every lane (shared memory).
 __device__ __forceinline__ float exact_score_lane(const float* r, const float* __restrict__ c, int d) {

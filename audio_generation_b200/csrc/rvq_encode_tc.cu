@@ -63,9 +63,11 @@ struct EncParams {
     float* dbg_scores;                // [128, Kpad] (bring-up hook) or null
     float* dbg_rowscale;              // [128] or null
     unsigned long long* prof;         // [16] cycle / event counters (RVQ_PROFILE=1) or null
-    int exp;                          // timing experiments (RVQ_EXP, results invalid when != 0)
-    int one;                          // the constant 1, opaque to the compiler (see merge_pair)
 };
+
+// Candidate set of one scan group for one frame, factorised: up to three loads (`it`, 9 bits each) x a 16-bit
+// column mask.  bits 27-28 = number of loads, bit 31 = OVER (more loads than kept, or no usable filter result).
+constexpr uint32_t G_OVER = 0x80000000u;
 
 struct __align__(16) Misc {
     uint64_t full[MAX_STAGES_RING], empty[MAX_STAGES_RING], tmem_full[2], tmem_empty[2], a_ready[2], scan_done[2];
@@ -74,14 +76,14 @@ struct __align__(16) Misc {
     uint32_t tmem_base;
     int dirty_count[2];
     float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
-    int cand[2][3][TILE_M], ncand[2][TILE_M];
+    float grp_best[2][2][TILE_M];            // [job parity][scan group][frame]: best score the group saw
+    uint32_t g_rows[2][2][TILE_M];           // [slot][group][frame]: loads that may hold a candidate
+    uint16_t g_cols[2][2][TILE_M];           // [slot][group][frame]: columns that may hold a candidate
+    uint16_t dirty_cols[2][TILE_M];          // per exact-scan frame: columns to scan
+    int win[2][TILE_M];                      // [slot][frame]: selected code, -1 = exact scan pending
     int dirty_rows[2][TILE_M];
-    uint32_t dirty_mask[2][TILE_M];  // per fallback frame: chunks that may hide a candidate
-    uint32_t mrg_mask[TILE_M];
     int score_rows[2][TILE_M];
     int score_count[2];
-    float mrg_v[5][TILE_M];
-    int mrg_k[3][TILE_M];
     float dirty_s[8];
     int dirty_k[8];
     double commit_acc[MAX_NQ];
@@ -310,64 +312,6 @@ __device__ __forceinline__ void apply_two_rows_128(const EncParams& p, Misc* mis
     }
 }
 
-// One frame with NP float4 pieces per lane (d = 32*NP), all loads of the frame in flight together.
-// Scalar-argument twin of apply_rows<1, NP/4> (kept separate: simpler code for the compiler).
-template <int NP>
-__device__ __forceinline__ void apply_row_fixed(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt,
-                                                int sl, int row, bool active, bool row_valid, int kwin, int q_abs,
-                                                int next_q_abs, int sub, float* sq_out) {
-    constexpr int d = 32 * NP;
-    const bool write_a = next_q_abs >= 0;
-    float sb = 1.f, cnmax = 0.f, sa = 0.f;
-    int a = 0, b = 0;
-    bool force_exact = false;
-    if (write_a) {
-        const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
-        sb = mq[0];
-        cnmax = mq[1];
-        b = ilog2f_floor(sb);
-        a = pick_row_exp(misc->row_amax[sl][row] + p.cb_meta[(size_t)q_abs * META_STRIDE + 2], b, force_exact);
-        sa = exp2i(a);
-    }
-    float* rrow = rt.at(row, sub * 4);
-    const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d + sub * 4;
-    float4 rv[NP], cv[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) rv[i] = *reinterpret_cast<const float4*>(rrow + i * 32);
-#pragma unroll
-    for (int i = 0; i < NP; ++i) cv[i] = ldg_nc_v4(cw + i * 32);
-    float* ssum = (p.stats_sum && row_valid && active) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d + sub * 4
-                                                       : nullptr;
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        if (ssum) red_add_v4(ssum + i * 32, rv[i]);
-        float4 nr;
-        nr.x = rv[i].x - cv[i].x;
-        nr.y = rv[i].y - cv[i].y;
-        nr.z = rv[i].z - cv[i].z;
-        nr.w = rv[i].w - cv[i].w;
-        sq = fmaf(nr.x, nr.x, sq);
-        sq = fmaf(nr.y, nr.y, sq);
-        sq = fmaf(nr.z, nr.z, sq);
-        sq = fmaf(nr.w, nr.w, sq);
-        if (active) {
-            *reinterpret_cast<float4*>(rrow + i * 32) = nr;
-            if (write_a) store_a4(smem_a, row, sub * 4 + i * 32, nr, sa);
-        }
-    }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    *sq_out = sq;
-    if (active && sub == 0) {
-        misc->row_amax[sl][row] = sqrtf(sq) * 1.00002f;
-        if (write_a) {
-            if (!isfinite(sq)) force_exact = true;
-            write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
-        }
-    }
-}
-
 // Stage-0 initialisation of one frame by an 8-lane group: x -> residual scratch, exact max -> operand scale,
 // fp16 operand row and row constants of the first stage (two passes: the scale needs the row maximum).
 __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
@@ -406,84 +350,76 @@ __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t
     }
 }
 
-__device__ __forceinline__ bool less_vk(float v, int k, float bv, int bk) { return (v < bv) || (v == bv && k < bk); }
+// ---------------------------------------------------------------------------------------------------------
+// Two-dimensional running minimum.  The codes a scan thread sees in one stage are laid out as a grid:
+// grid row = one TMEM load of 16 consecutive codes (`it` = code / 16), grid column = position j inside the load.
+// Per score the thread pays one FFMA (norm) and one FMNMX into the column minimum Cm[j]; per load it reduces
+// the 16 scores to the load's minimum with 3-input minima, replaces its low 9 mantissa bits by `it` and
+// inserts it into a sorted triple (+ fourth value).  No per-score index bookkeeping, no per-score sort.
+//   * the best score is min_j Cm[j]; it sits at (argmin over loads, argmin over columns);
+//   * every code scoring <= T lies in a load whose minimum is <= T AND in a column whose minimum is <= T,
+//     so {loads <= T} x {columns <= T} is a superset of the candidates: it is re-scored exactly.
+constexpr uint32_t IT_MASK = 0x1FFu;  // 32 chunks x 16 loads
 
-// running best-three (value, code), fourth value and the bound H on codes hidden behind a chunk's third
-struct Top4 {
-    float v1, v2, v3, v4, hid;
-    int k1, k2, k3;
-    __device__ __forceinline__ void reset() {
-        v1 = v2 = v3 = v4 = hid = BIG;
-        k1 = k2 = k3 = 0x7fffffff;
-    }
-    __device__ __forceinline__ void insert(float v, int k) {
-        if (less_vk(v, k, v1, k1)) {
-            v4 = v3;
-            v3 = v2;
-            k3 = k2;
-            v2 = v1;
-            k2 = k1;
-            v1 = v;
-            k1 = k;
-        } else if (less_vk(v, k, v2, k2)) {
-            v4 = v3;
-            v3 = v2;
-            k3 = k2;
-            v2 = v;
-            k2 = k;
-        } else if (less_vk(v, k, v3, k3)) {
-            v4 = v3;
-            v3 = v;
-            k3 = k;
-        } else {
-            v4 = fminf(v4, v);
-        }
-    }
-};
-
-// sorted triple (m1 <= m2 <= m3) <- three smallest of {m1, m2, m3, a, b}: 8 FMNMX per pair of scores
-// `one` is the runtime constant 1 (kernel parameter): hi = a + b - lo is computed on the bit patterns with two
-// IMADs (FMA pipe) instead of one more FMNMX on the ALU pipe, which is the pipe that bounds the epilogue; a
-// literal 1 would let ptxas turn them back into ALU-pipe IADD3s.
-__device__ __forceinline__ void merge_pair(float a, float b, float& m1, float& m2, float& m3, int one) {
-    const float lo = fminf(a, b);
-    const int t_ = __float_as_int(a) * one + __float_as_int(b);
-    const float hi = __int_as_float(t_ - __float_as_int(lo) * one);
-    const float n3 = fminf(fminf(m3, fmaxf(m2, lo)), fmaxf(m1, hi));
-    const float n2 = fminf(fminf(m2, fmaxf(m1, lo)), hi);
-    m1 = fminf(m1, lo);
-    m2 = n2;
-    m3 = n3;
-}
-
-// 16 accumulator columns of one frame -> packed (score | column) values merged into TWO independent sorted
-// triples (A takes columns 0,1,4,5,..., B takes 2,3,6,7,...) so that consecutive merges do not wait on each
-// other.  colpack holds the four column bytes {c+3, c+2, c+1, c} of the first group; one PRMT per score
-// replaces the low mantissa byte by its column.
-__device__ __forceinline__ void scan16(const uint32_t (&v)[16], const float* __restrict__ nptr, float na,
-                                       uint32_t colpack, float (&A)[3], float (&B)[3], float* dbg, int one) {
+__device__ __forceinline__ void scan16_2d(const uint32_t (&v)[16], const float* __restrict__ nptr, float na,
+                                          uint32_t it, float (&Cm)[16], float& m1, float& m2, float& m3, float& m4,
+                                          float* dbg) {
+    float s[16];
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
         const float4 nn = *reinterpret_cast<const float4*>(nptr + j);  // shared memory, warp-uniform
-        const float s0 = fmaf(na, nn.x, __uint_as_float(v[j + 0]));
-        const float s1 = fmaf(na, nn.y, __uint_as_float(v[j + 1]));
-        const float s2 = fmaf(na, nn.z, __uint_as_float(v[j + 2]));
-        const float s3 = fmaf(na, nn.w, __uint_as_float(v[j + 3]));
-        if (dbg) {
-            dbg[j + 0] = s0;
-            dbg[j + 1] = s1;
-            dbg[j + 2] = s2;
-            dbg[j + 3] = s3;
-        }
-        const uint32_t cp = colpack + (uint32_t)j * 0x01010101u;
-        const float p0 = __uint_as_float(__byte_perm(__float_as_uint(s0), cp, 0x3214));
-        const float p1 = __uint_as_float(__byte_perm(__float_as_uint(s1), cp, 0x3215));
-        const float p2 = __uint_as_float(__byte_perm(__float_as_uint(s2), cp, 0x3216));
-        const float p3 = __uint_as_float(__byte_perm(__float_as_uint(s3), cp, 0x3217));
-        merge_pair(p0, p1, A[0], A[1], A[2], one);
-        merge_pair(p2, p3, B[0], B[1], B[2], one);
+        s[j + 0] = fmaf(na, nn.x, __uint_as_float(v[j + 0]));
+        s[j + 1] = fmaf(na, nn.y, __uint_as_float(v[j + 1]));
+        s[j + 2] = fmaf(na, nn.z, __uint_as_float(v[j + 2]));
+        s[j + 3] = fmaf(na, nn.w, __uint_as_float(v[j + 3]));
     }
+    if (dbg) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dbg[j] = s[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) Cm[j] = fminf(Cm[j], s[j]);
+    float r = fminf(fminf(s[0], s[1]), s[2]);
+#pragma unroll
+    for (int j = 3; j < 15; j += 2) r = fminf(fminf(r, s[j]), s[j + 1]);
+    r = fminf(r, s[15]);
+    const float rp = __uint_as_float((__float_as_uint(r) & ~IT_MASK) | it);
+    const float t = fmaxf(m1, rp);
+    m1 = fminf(m1, rp);
+    const float u = fmaxf(m2, t);
+    m2 = fminf(m2, t);
+    const float w = fmaxf(m3, u);
+    m3 = fminf(m3, u);
+    m4 = fminf(m4, w);
 }
+
+// enumeration of {loads} x {columns} of both scan groups
+struct CandSet {
+    uint32_t r[2], c[2];
+    int n[2], pc[2];
+    __device__ __forceinline__ CandSet(uint32_t r0, uint32_t c0, uint32_t r1, uint32_t c1) {
+        r[0] = r0;
+        r[1] = r1;
+        c[0] = c0;
+        c[1] = c1;
+        pc[0] = __popc(c0);
+        pc[1] = __popc(c1);
+        n[0] = (int)((r0 >> 27) & 3u) * pc[0];
+        n[1] = (int)((r1 >> 27) & 3u) * pc[1];
+    }
+    __device__ __forceinline__ int total() const { return n[0] + n[1]; }
+    // code number e of the set, clamped into [0, kmax] (out-of-range e, or an empty set, gives a harmless code)
+    __device__ __forceinline__ int code(int e, int kmax) const {
+        e = max(0, min(e, total() - 1));
+        const int g = e >= n[0];
+        e -= g ? n[0] : 0;
+        const int pcg = max(pc[g], 1);
+        const int a = e / pcg, jj = e - a * pcg;
+        const uint32_t it = (r[g] >> (9 * a)) & IT_MASK;
+        const int k = (int)(it * 16u) + (int)(__fns(c[g], 0, jj + 1) & 15u);
+        return max(0, min(k, kmax));
+    }
+};
 
 // job = (tile slot, tile, stage); every role walks the same sequence.
 struct JobIter {
@@ -558,8 +494,10 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     // Register budget: 640 threads x 96 = 61440 registers at launch.  setmaxnreg.inc can only take what
     // setmaxnreg.dec released inside this CTA, so the totals after rebalancing must not exceed the launch
     // allocation: 40*128 (control) + 88*256 (scan) + 128*256 (update) = 60416 <= 61440.
+    // setmaxnreg is warpgroup-aligned: the four warps of a warpgroup must execute the SAME instruction, so the
+    // control warpgroup releases its registers once, before its warps split into roles.
+    if (warp < SCAN_WARP0) reg_dealloc<40>();
     if (warp == 0) {
-        reg_dealloc<40>();
         // =========================================================== TMA producer (codebook slices)
         if (lane == 0) {
             uint32_t it = 0;
@@ -577,7 +515,6 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             }
         }
     } else if (warp == 1) {
-        reg_dealloc<40>();
         // =========================================================== MMA issuer
         const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CHUNK_N);
         uint32_t it = 0, g = 0, aphase = 0;
@@ -619,17 +556,15 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             }
         }
     } else if (warp < SCAN_WARP0) {
-        reg_dealloc<40>();
     } else if (warp < UPD_WARP0) {
         reg_dealloc<88>();
         // =========================================================== scan groups (argmin epilogue)
         const int e = threadIdx.x - SCAN_WARP0 * 32;  // 0..255
         const int grp = e >> 7;                       // scan group = accumulator buffer
         const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
-        uint32_t g = 0, aphase = 0;
-        const int one = p.one;
+        uint32_t g = 0, aphase = 0, jpar = 0;
         long long t_scan = 0, t_wait = 0, t_full = 0;
-        for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+        for (JobIter job(n_local, nq, nslots); job.valid(); job.next(), jpar ^= 1u) {
             const int sl = job.slot % nslots;
             const int q_abs = p.q_begin + job.q;
             long long t0 = clock64();
@@ -637,9 +572,10 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             aphase ^= 1u << sl;
             const float na = misc->row_na[sl][my_row];
             const float delta = misc->row_delta[sl][my_row];
-            Top4 G;
-            G.reset();
-            uint32_t cmask = 0;  // chunks whose third-best score is within delta of the running best (superset)
+            float Cm[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) Cm[j] = BIG;
+            float m1 = BIG, m2 = BIG, m3 = BIG, m4 = BIG;
             long long t1 = clock64();
             t_wait += t1 - t0;
             for (int c = 0; c < n_chunks; ++c, ++g) {
@@ -649,115 +585,57 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 mbar_wait(&misc->norm_full[grp], (g >> 1) & 1);
                 tc_fence_after_sync();
                 t_full += clock64() - tw0;
-                float A[3] = {BIG, BIG, BIG}, B[3] = {BIG, BIG, BIG};
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CHUNK_N;
                 const float* nptr = misc->norms[grp];
                 float* dbg = nullptr;
                 if (kDebug && p.dbg_scores && job.i == 0 && job.q == 0)
                     dbg = p.dbg_scores + (size_t)my_row * p.Kpad + c * CHUNK_N;
                 // 16 columns per TMEM load, double buffered; the loop body (32 columns) stays small enough for
-                // the instruction cache (a fully unrolled 256-column body does not)
+                // the instruction cache
                 uint32_t va[16], vb[16];
                 tmem_ld_32x16(taddr, va);
-                uint32_t colpack = 0x03020100u;
+                uint32_t it = (uint32_t)c * (CHUNK_N / 16);
 #pragma unroll 1
-                for (int cb = 0; cb < CHUNK_N; cb += 32) {
+                for (int cb = 0; cb < CHUNK_N; cb += 32, it += 2) {
                     tmem_ld_wait();
                     tmem_ld_32x16(taddr + cb + 16, vb);
-                    scan16(va, nptr + cb, na, colpack, A, B, kDebug && dbg ? dbg + cb : nullptr, one);
+                    scan16_2d(va, nptr + cb, na, it, Cm, m1, m2, m3, m4, kDebug && dbg ? dbg + cb : nullptr);
                     tmem_ld_wait();
                     if (cb + 32 < CHUNK_N) tmem_ld_32x16(taddr + cb + 32, va);
-                    scan16(vb, nptr + cb + 16, na, colpack + 0x10101010u, A, B,
-                           kDebug && dbg ? dbg + cb + 16 : nullptr, one);
-                    colpack += 0x20202020u;
+                    scan16_2d(vb, nptr + cb + 16, na, it + 1, Cm, m1, m2, m3, m4,
+                              kDebug && dbg ? dbg + cb + 16 : nullptr);
                 }
-                // the two triples -> one
-                merge_pair(B[0], B[1], A[0], A[1], A[2], one);
-                {
-                    const float n3 = fminf(A[2], fmaxf(A[1], B[2]));
-                    const float n2 = fminf(A[1], fmaxf(A[0], B[2]));
-                    A[0] = fminf(A[0], B[2]);
-                    A[1] = n2;
-                    A[2] = n3;
-                }
-                const float m1 = A[0], m2 = A[1], m3 = A[2];
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&misc->tmem_empty[grp]);
-                // chunk-local best three -> running best of the stage (values with the column bits cleared)
-                const uint32_t b1 = __float_as_uint(m1), b2 = __float_as_uint(m2), b3 = __float_as_uint(m3);
-                G.insert(__uint_as_float(b1 & 0xFFFFFF00u), c * CHUNK_N + (int)(b1 & 0xFFu));
-                G.insert(__uint_as_float(b2 & 0xFFFFFF00u), c * CHUNK_N + (int)(b2 & 0xFFu));
-                G.insert(__uint_as_float(b3 & 0xFFFFFF00u), c * CHUNK_N + (int)(b3 & 0xFFu));
-                // every code of this chunk that is not one of its three best scores at least its third best
-                G.hid = fminf(G.hid, __uint_as_float(b3 & 0xFFFFFF00u));
-                // the running best only improves, so a chunk that is clean against it stays clean
-                if (!(__uint_as_float(b3 & 0xFFFFFF00u) > G.v1 + delta)) cmask |= 1u << (c & 31);
             }
-            // ---------------- merge the two groups' candidates, decide how many need an exact score
-            if (grp == 1) {
-                misc->mrg_v[0][my_row] = G.v1;
-                misc->mrg_v[1][my_row] = G.v2;
-                misc->mrg_v[2][my_row] = G.v3;
-                misc->mrg_v[3][my_row] = G.v4;
-                misc->mrg_v[4][my_row] = G.hid;
-                misc->mrg_k[0][my_row] = G.k1;
-                misc->mrg_k[1][my_row] = G.k2;
-                misc->mrg_k[2][my_row] = G.k3;
-                misc->mrg_mask[my_row] = cmask;
-            }
+            // ---------------- stage end: exchange the groups' best scores, list this group's candidates
+            float vb_ = fminf(fminf(Cm[0], Cm[1]), Cm[2]);
+#pragma unroll
+            for (int j = 3; j < 15; j += 2) vb_ = fminf(fminf(vb_, Cm[j]), Cm[j + 1]);
+            vb_ = fminf(vb_, Cm[15]);
+            misc->grp_best[jpar][grp][my_row] = vb_;
             named_bar_sync(BAR_SCAN, SCAN_THREADS);
-            if (grp == 0) {
-                G.insert(misc->mrg_v[0][my_row], misc->mrg_k[0][my_row]);
-                G.insert(misc->mrg_v[1][my_row], misc->mrg_k[1][my_row]);
-                G.insert(misc->mrg_v[2][my_row], misc->mrg_k[2][my_row]);
-                G.v4 = fminf(G.v4, misc->mrg_v[3][my_row]);
-                G.hid = fminf(G.hid, misc->mrg_v[4][my_row]);
-                const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
-                // Certificate: a code can beat the approximate best only if its approximate score is <= lim.
-                // Codes outside the kept triples score >= hid; hid >= v3 always, and hid >= v4 unless the three
-                // best share one chunk.
-                int nc;
-                if (p.exp) {
-                    G.v1 = 0.f;
-                    G.k1 = my_row;
-                    G.v2 = G.v3 = G.v4 = G.hid = BIG;
-                }
-                const float lim = G.v1 + delta;
-                if (!(G.v1 < BIG) || G.k1 >= Kv || !(lim == lim)) {
-                    nc = 4;  // no usable filter result (NaN / overflow): exact scan
-                } else if (G.v2 > lim) {
-                    nc = 1;
-                } else if (G.v3 > lim && G.k2 < Kv) {
-                    nc = 2;
-                } else if (G.v4 > lim && G.hid > lim && G.k2 < Kv && G.k3 < Kv) {
-                    nc = 3;
-                } else {
-                    nc = 4;
-                }
-                misc->cand[sl][0][my_row] = G.k1;
-                misc->cand[sl][1][my_row] = G.k2;
-                misc->cand[sl][2][my_row] = G.k3;
-                misc->ncand[sl][my_row] = nc;
-                if (nc == 4) {
-                    const int pos = atomicAdd(&misc->dirty_count[sl], 1);
-                    misc->dirty_rows[sl][pos] = my_row;
-                    uint32_t mk = cmask | misc->mrg_mask[my_row];
-                    if (n_chunks > 32 || !(G.v1 < BIG) || !(lim == lim)) {
-                        mk = 0xFFFFFFFFu;  // more chunks than mask bits, or no usable filter result: scan everything
-                    } else {
-                        if (G.k1 < Kv) mk |= 1u << (G.k1 / CHUNK_N);
-                        if (G.k2 < Kv) mk |= 1u << (G.k2 / CHUNK_N);
-                        if (G.k3 < Kv) mk |= 1u << (G.k3 / CHUNK_N);
-                    }
-                    const int nch = (Kv + CHUNK_N - 1) / CHUNK_N;
-                    misc->dirty_mask[sl][pos] = nch >= 32 ? mk : (mk & ((1u << nch) - 1u));
-                } else if (nc >= 2) {
-                    const int pos = atomicAdd(&misc->score_count[sl], 1);
-                    misc->score_rows[sl][pos] = my_row;
-                }
+            {
+                const float best = fminf(vb_, misc->grp_best[jpar][grp ^ 1][my_row]);
+                // Certificate: a code can be the exact argmin only if its approximate score is <= T.
+                const float T = best + delta;
+                // load minima carry `it` in their low 9 mantissa bits: |packed - r| <= 2^-14 |r|, and every load
+                // minimum r of interest lies in [best, T], so |r| <= |best| + delta
+                const float T2 = T + (fabsf(best) + 2.f * delta) * 1.220703125e-4f;
+                // NaN / overflow / forced exact (no usable filter result), or more than three loads in reach
+                const bool nofilter = !(best < BIG) || !(T2 < BIG);
+                const bool over = nofilter || (m4 <= T2);
+                const uint32_t nr = (uint32_t)(m1 <= T2) + (uint32_t)(m2 <= T2) + (uint32_t)(m3 <= T2);
+                uint32_t cols = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cols |= (Cm[j] <= T) ? (1u << j) : 0u;
+                if (nofilter) cols = 0xFFFFu;
+                const uint32_t rows = (__float_as_uint(m1) & IT_MASK) | ((__float_as_uint(m2) & IT_MASK) << 9) |
+                                      ((__float_as_uint(m3) & IT_MASK) << 18) | (nr << 27) | (over ? G_OVER : 0u);
+                misc->g_rows[sl][grp][my_row] = rows;
+                misc->g_cols[sl][grp][my_row] = (uint16_t)cols;
             }
-            named_bar_sync(BAR_SCAN, SCAN_THREADS);  // mrg buffers may be rewritten by the next job
             mbar_arrive(&misc->scan_done[sl]);
             t_scan += clock64() - t1;
         }
@@ -826,29 +704,58 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             t_wait += t1 - t0;
             const int next_q_abs = (q + 1 < nq) ? q_abs + 1 : -1;
             const float* cbq = p.cb + (size_t)q_abs * p.K * d;
-            // ---------------- exact re-rank of the frames with 2 or 3 candidates (compacted list)
+            // ---------------- classify the frames: certified (one candidate), re-rank list, exact-scan list
             const long long ts0 = clock64();
+            const int Kv_q = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
+            if (u < TILE_M) {
+                const uint32_t r0 = misc->g_rows[sl][0][u], r1 = misc->g_rows[sl][1][u];
+                const uint32_t c0 = misc->g_cols[sl][0][u], c1 = misc->g_cols[sl][1][u];
+                const int n0 = (int)((r0 >> 27) & 3u) * __popc(c0), n1 = (int)((r1 >> 27) & 3u) * __popc(c1);
+                int w = -1;
+                if (((r0 | r1) & G_OVER) || n0 + n1 == 0) {
+                    const int pos = atomicAdd(&misc->dirty_count[sl], 1);
+                    misc->dirty_rows[sl][pos] = u;
+                    misc->dirty_cols[sl][pos] = (uint16_t)((c0 | c1) ? (c0 | c1) : 0xFFFFu);
+                } else if (n0 + n1 == 1) {
+                    w = n0 ? (int)((r0 & IT_MASK) * 16u) + __ffs(c0) - 1 : (int)((r1 & IT_MASK) * 16u) + __ffs(c1) - 1;
+                    if (w >= Kv_q) w = 0;  // cannot happen (padding codes score 2^100); keeps the gather in bounds
+                } else {
+                    misc->score_rows[sl][atomicAdd(&misc->score_count[sl], 1)] = u;
+                    w = 0;  // replaced by the re-rank below
+                }
+                misc->win[sl][u] = w;
+            }
+            named_bar_sync(BAR_UPD, UPD_THREADS);
+            // ---------------- exact re-rank of the frames with several candidates (compacted list)
             const int n_score = misc->score_count[sl];
-            for (int base = 0; base < (p.exp == 4 ? 0 : n_score); base += ROWS_PER_PASS) {
+            for (int base = 0; base < n_score; base += ROWS_PER_PASS) {
                 const int i = base + slot16;
                 const bool sc = i < n_score;
                 const int row = misc->score_rows[sl][sc ? i : 0];
-                const int nc = misc->ncand[sl][row];
-                const int c1 = misc->cand[sl][0][row], c2 = misc->cand[sl][1][row];
-                const int c3 = (nc == 3) ? misc->cand[sl][2][row] : c1;
-                const float* cc[3] = {cbq + (size_t)c1 * d, cbq + (size_t)c2 * d, cbq + (size_t)c3 * d};
-                float s[3];
-                exact_score8_n<3>(rt.at(row, 0), cc, d, sub, s);
-                if (sc && sub == 0) {
-                    float bs = s[0];
-                    int kwin = c1;
-                    if (better(s[1], c2, bs, kwin)) {
-                        bs = s[1];
+                const CandSet cs(misc->g_rows[sl][0][row], misc->g_cols[sl][0][row], misc->g_rows[sl][1][row],
+                                 misc->g_cols[sl][1][row]);
+                const int nc = sc ? cs.total() : 0;
+                int nc_max = nc;  // the whole warp walks the longest list of its four frames
+                nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, 8));
+                nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, 16));
+                float bs = __int_as_float(0x7f800000);
+                int kwin = 0x7fffffff;
+#pragma unroll 1
+                for (int j = 0; j < nc_max; j += 2) {
+                    const int c1 = cs.code(j, Kv_q - 1), c2 = cs.code(j + 1, Kv_q - 1);
+                    const float* cc[2] = {cbq + (size_t)c1 * d, cbq + (size_t)c2 * d};
+                    float sv[2];
+                    exact_score8_n<2>(rt.at(row, 0), cc, d, sub, sv);
+                    if (better(sv[0], c1, bs, kwin)) {
+                        bs = sv[0];
+                        kwin = c1;
+                    }
+                    if (better(sv[1], c2, bs, kwin)) {
+                        bs = sv[1];
                         kwin = c2;
                     }
-                    if (nc == 3 && better(s[2], c3, bs, kwin)) kwin = c3;
-                    misc->cand[sl][0][row] = kwin;
                 }
+                if (sc && sub == 0) misc->win[sl][row] = kwin;
                 ++n_score_pass;
             }
             if (n_score > 0) named_bar_sync(BAR_UPD, UPD_THREADS);  // winners visible to the applying groups
@@ -863,23 +770,12 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
             };
-            if (p.exp == 4) {
-            } else if (d == 256) {
-#pragma unroll 1
-                for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
-                    const bool active = misc->ncand[sl][row] != 4;
-                    const int kwin = active ? misc->cand[sl][0][row] : 0;
-                    float sq;
-                    apply_row_fixed<8>(p, misc, a_tile, rt, sl, row, active, n0 + row < p.N, kwin, q_abs, next_q_abs,
-                                       sub, &sq);
-                    post_row(row, active, kwin, sq);
-                }
-            } else if (d == 128) {
+            if (d == 128) {
 #pragma unroll 1
                 for (int r0 = slot16; r0 < TILE_M; r0 += 2 * ROWS_PER_PASS) {
                     const int r1 = r0 + ROWS_PER_PASS;
-                    const bool a0 = misc->ncand[sl][r0] != 4, a1 = misc->ncand[sl][r1] != 4;
-                    const int k0 = a0 ? misc->cand[sl][0][r0] : 0, k1 = a1 ? misc->cand[sl][0][r1] : 0;
+                    const bool a0 = misc->win[sl][r0] >= 0, a1 = misc->win[sl][r1] >= 0;
+                    const int k0 = a0 ? misc->win[sl][r0] : 0, k1 = a1 ? misc->win[sl][r1] : 0;
                     float sq0, sq1;
                     apply_two_rows_128(p, misc, a_tile, rt, sl, r0, r1, a0, a1, n0 + r0 < p.N, n0 + r1 < p.N, k0, k1,
                                        q_abs, next_q_abs, sub, sq0, sq1);
@@ -889,8 +785,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             } else {
 #pragma unroll 1
                 for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
-                    const bool active = misc->ncand[sl][row] != 4;
-                    const int kwin = active ? misc->cand[sl][0][row] : 0;
+                    const bool active = misc->win[sl][row] >= 0;
+                    const int kwin = active ? misc->win[sl][row] : 0;
                     float sq;
                     apply_row(p, misc, a_tile, rt, sl, row, active, n0 + row < p.N, kwin, q_abs, next_q_abs, sub, &sq);
                     post_row(row, active, kwin, sq);
@@ -909,18 +805,12 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
 #pragma unroll 1
                 for (int i = 0; i < n_dirty; ++i) {
                     const int row = misc->dirty_rows[sl][i];
-                    // only chunks whose third-best score could be inside the margin can hide a candidate
-                    // (plus the chunks of the three kept candidates, which the scan marked as well)
-                    const uint32_t cmask = misc->dirty_mask[sl][i];
-                    ScoreIdx b{__int_as_float(0x7f800000), 0x7fffffff};
-                    for (uint32_t mm = cmask; mm; mm &= mm - 1) {
-                        const int cbeg = (__ffs(mm) - 1) * CHUNK_N;
-                        const int cend = min(Kv, cbeg + CHUNK_N);
-                        const int per_c = (CHUNK_N + UPD_WARPS - 1) / UPD_WARPS;
-                        const int k0 = min(cend, cbeg + uwarp * per_c), k1 = min(cend, k0 + per_c);
-                        const ScoreIdx bc = exact_scan_warp(rt.at(row, 0), cbq, d, k0, k1, lane);
-                        if (better(bc.s, bc.k, b.s, b.k)) b = bc;
-                    }
+                    // only the columns whose minimum is in reach can hold a candidate; each update warp scans
+                    // an equal share of the stage's loads
+                    const uint32_t cols = misc->dirty_cols[sl][i];
+                    const int n_it = (Kv + 15) / 16, per_w = (n_it + UPD_WARPS - 1) / UPD_WARPS;
+                    const int it0 = min(n_it, uwarp * per_w), it1 = min(n_it, it0 + per_w);
+                    const ScoreIdx b = exact_scan_cols(rt.at(row, 0), cbq, d, it0, it1, cols, Kv, lane);
                     if (lane == 0) {
                         misc->dirty_s[uwarp] = b.s;
                         misc->dirty_k[uwarp] = b.k;
@@ -1140,9 +1030,6 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     p.off_misc = sp.off_misc;
     p.dbg_scores = dbg_scores;
     p.dbg_rowscale = dbg_rowscale;
-    static const int exp_mode = getenv("RVQ_EXP") ? atoi(getenv("RVQ_EXP")) : 0;
-    p.exp = exp_mode;
-    p.one = 1;
     static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
     if (want_prof && ws && ws_bytes >= 128) {
         // counters live in the LAST 128 bytes of the workspace
