@@ -1,6 +1,7 @@
 // rvq_abi.cu -- extern "C" entry points of librvq_sm100a.so (declared in include/rvq_sm100a.h):
 // argument checking, device gate, error state, dispatch to the kernels.  No torch types cross this file.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -28,6 +29,11 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
                   const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
                   float* stats_cnt, void* ws, size_t ws_bytes, float* dbg_scores, float* dbg_rowscale,
                   cudaStream_t st);
+bool rvq_tr_supported(int d);
+int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d, int nq,
+                  int K, int q_begin, const float* cb, const void* cb_op, int nq_total, const float* cb_norm,
+                  const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
+                  float* stats_cnt, void* ws, size_t ws_bytes, cudaStream_t st);
 int rvq_launch_exact_scan(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d,
                           int nq, int K, const float* cb, const float* meta, float* xq, long long* idx,
                           double* commit_sq, float* stats_sum, float* stats_cnt, cudaStream_t st);
@@ -108,6 +114,11 @@ extern "C" int rvq_encode(const float* x, long long N, long long L, long long st
         set_error("rvq_encode: cb_op is null");
         return RVQ_ERR_ARG;
     }
+    // d <= 128: residual resident in tensor memory (rvq_encode_tr.cu); RVQ_KERNEL=tc forces the generic kernel
+    static const bool force_tc = getenv("RVQ_KERNEL") && !strcmp(getenv("RVQ_KERNEL"), "tc");
+    if (rvq_tr_supported(d) && !force_tc)
+        return rvq_launch_tr(x, N, L, stride_b, stride_l, stride_d, d, nq_use, K, 0, cb, cb_op, nq_use, cb_norm, cb_meta,
+                             xq, idx, commit_sq, stats_sum, stats_cnt, ws, ws_bytes, st);
     // the TMA descriptor spans stages [0, nq_use): later stages are never addressed
     return rvq_launch_tc(x, N, L, stride_b, stride_l, stride_d, d, nq_use, K, 0, cb, cb_op, nq_use, cb_norm, cb_meta,
                          xq, idx, commit_sq, stats_sum, stats_cnt, ws, ws_bytes, nullptr, nullptr, st);

@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "exact.cuh"
+#include "encode_common.cuh"
 
 namespace rvq {
 
@@ -33,16 +34,9 @@ constexpr int UPD_THREADS = 256;
 constexpr int NUM_THREADS = UPD_WARP0 * 32 + UPD_THREADS;  // 640
 constexpr int MAX_STAGES_RING = 6;
 constexpr int MAX_NQ = 64;
-constexpr uint32_t A_SLICE_BYTES = TILE_M * KSLICE * 2;   // 16 KiB
 constexpr uint32_t B_STAGE_BYTES = CHUNK_N * KSLICE * 2;  // 32 KiB
 constexpr uint32_t BAR_SCAN = 1;  // named barrier of the 256 scan threads
 constexpr uint32_t BAR_UPD = 2;   // named barrier of the update threads
-constexpr float BIG = 3.0e38f;
-
-struct RowAddrT {
-    long long L, sb, sl, sd;
-    __device__ __forceinline__ long long row(long long n) const { return (n / L) * sb + (n % L) * sl; }
-};
 
 struct EncParams {
     const float* x;
@@ -65,14 +59,10 @@ struct EncParams {
     unsigned long long* prof;         // [16] cycle / event counters (RVQ_PROFILE=1) or null
 };
 
-// Candidate set of one scan group for one frame, factorised: up to three loads (`it`, 9 bits each) x a 16-bit
-// column mask.  bits 27-28 = number of loads, bit 31 = OVER (more loads than kept, or no usable filter result).
-constexpr uint32_t G_OVER = 0x80000000u;
-
 struct __align__(16) Misc {
     uint64_t full[MAX_STAGES_RING], empty[MAX_STAGES_RING], tmem_full[2], tmem_empty[2], a_ready[2], scan_done[2];
     uint64_t norm_full[2];
-    float norms[2][CHUNK_N];  // scaled ||c||^2 of the chunk in each accumulator buffer (bulk-copied)
+    alignas(16) float norms[2][CHUNK_N];  // scaled ||c||^2 of the chunk in each accumulator buffer (bulk-copied)
     uint32_t tmem_base;
     int dirty_count[2];
     float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
@@ -97,40 +87,14 @@ struct RTile {
     __device__ __forceinline__ float* at(int row, int col) const { return base + (size_t)row * pitch + col; }
 };
 
-// byte offset of fp16 element (row, col) inside the A tile (d/64 slices of [128 rows x 128 B], SWIZZLE_128B)
-__device__ __forceinline__ uint32_t a_tile_offset(int row, int col) {
-    const int slice = col >> 6, c = col & 63;
-    return (uint32_t)slice * A_SLICE_BYTES + (uint32_t)row * 128u + ((((uint32_t)c >> 3) ^ ((uint32_t)row & 7u)) << 4) +
-           (((uint32_t)c & 7u) << 1);
-}
-
 // per-row constants of the next stage from the new residual's norm and the operand scale
 __device__ __forceinline__ void write_row_consts(const EncParams& p, Misc* misc, int sl, int row, int d, float sq,
                                                  bool force_exact, int a, int b, float sb, float cnmax) {
-    const float sa = exp2i(a);
-    const float na = exp2i(max(-120, min(120, a - b)));
-    const float rs = sqrtf(sq) * 1.00002f * sa;  // scaled ||r||_2 (upper bound)
-    const float cs = cnmax * sb;                 // scaled max ||c||_2
-    // |approx - exact| (scaled units) <= 2^-9(1+..) rs cs  [fp16 rounding of both operands, Cauchy-Schwarz]
-    //   + 2^-15 |score|                                   [8 low mantissa bits replaced by the column]
-    //   + d 2^-14                                          [fp16 subnormal absolute error, accumulate slack]
-    const float E = 1.02f * 0.001953125f * rs * cs + 3.0517578125e-5f * (na * cs * cs + 2.f * rs * cs) +
-                    (float)d * 6.103515625e-5f;
-    float delta = 2.1f * E;
-    if (force_exact || !isfinite(delta)) delta = __int_as_float(0x7f800000);
+    float na, delta;
+    row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
     misc->row_na[sl][row] = na;
     misc->row_delta[sl][row] = delta;
-    if (p.dbg_rowscale) p.dbg_rowscale[row] = sa;
-}
-
-// operand scale exponent for a row whose entries are bounded by amax_bound, given the stage's b
-__device__ __forceinline__ int pick_row_exp(float amax_bound, int b, bool& force_exact) {
-    int a = b + ROW_OVER_CODE_MAX;
-    if (!isfinite(amax_bound)) force_exact = true;
-    if (amax_bound > 0.f && isfinite(amax_bound)) a = min(a, SCALE_TARGET_EXP - ilog2f_floor(amax_bound));
-    if (a < b - ROW_UNDER_CODE_MAX) force_exact = true;  // frame >= 2^40 x larger than the codes: no fp16 window
-    a = max(a, b - ROW_UNDER_CODE_MAX);
-    return max(-100, min(100, a));
+    if (p.dbg_rowscale) p.dbg_rowscale[row] = exp2i(a);
 }
 
 __device__ __forceinline__ void store_a4(uint8_t* smem_a, int row, int c, float4 v, float sa) {
@@ -349,107 +313,6 @@ __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t
         write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
     }
 }
-
-// ---------------------------------------------------------------------------------------------------------
-// Two-dimensional running minimum.  The codes a scan thread sees in one stage are laid out as a grid:
-// grid row = one TMEM load of 16 consecutive codes (`it` = code / 16), grid column = position j inside the load.
-// Per score the thread pays one FFMA (norm) and one FMNMX into the column minimum Cm[j]; per load it reduces
-// the 16 scores to the load's minimum with 3-input minima, replaces its low 9 mantissa bits by `it` and
-// inserts it into a sorted triple (+ fourth value).  No per-score index bookkeeping, no per-score sort.
-//   * the best score is min_j Cm[j]; it sits at (argmin over loads, argmin over columns);
-//   * every code scoring <= T lies in a load whose minimum is <= T AND in a column whose minimum is <= T,
-//     so {loads <= T} x {columns <= T} is a superset of the candidates: it is re-scored exactly.
-constexpr uint32_t IT_MASK = 0x1FFu;  // 32 chunks x 16 loads
-
-__device__ __forceinline__ void scan16_2d(const uint32_t (&v)[16], const float* __restrict__ nptr, float na,
-                                          uint32_t it, float (&Cm)[16], float& m1, float& m2, float& m3, float& m4,
-                                          float* dbg) {
-    float s[16];
-#pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-        const float4 nn = *reinterpret_cast<const float4*>(nptr + j);  // shared memory, warp-uniform
-        s[j + 0] = fmaf(na, nn.x, __uint_as_float(v[j + 0]));
-        s[j + 1] = fmaf(na, nn.y, __uint_as_float(v[j + 1]));
-        s[j + 2] = fmaf(na, nn.z, __uint_as_float(v[j + 2]));
-        s[j + 3] = fmaf(na, nn.w, __uint_as_float(v[j + 3]));
-    }
-    if (dbg) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) dbg[j] = s[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) Cm[j] = fminf(Cm[j], s[j]);
-    float r = fminf(fminf(s[0], s[1]), s[2]);
-#pragma unroll
-    for (int j = 3; j < 15; j += 2) r = fminf(fminf(r, s[j]), s[j + 1]);
-    r = fminf(r, s[15]);
-    const float rp = __uint_as_float((__float_as_uint(r) & ~IT_MASK) | it);
-    const float t = fmaxf(m1, rp);
-    m1 = fminf(m1, rp);
-    const float u = fmaxf(m2, t);
-    m2 = fminf(m2, t);
-    const float w = fmaxf(m3, u);
-    m3 = fminf(m3, u);
-    m4 = fminf(m4, w);
-}
-
-// enumeration of {loads} x {columns} of both scan groups
-struct CandSet {
-    uint32_t r[2], c[2];
-    int n[2], pc[2];
-    __device__ __forceinline__ CandSet(uint32_t r0, uint32_t c0, uint32_t r1, uint32_t c1) {
-        r[0] = r0;
-        r[1] = r1;
-        c[0] = c0;
-        c[1] = c1;
-        pc[0] = __popc(c0);
-        pc[1] = __popc(c1);
-        n[0] = (int)((r0 >> 27) & 3u) * pc[0];
-        n[1] = (int)((r1 >> 27) & 3u) * pc[1];
-    }
-    __device__ __forceinline__ int total() const { return n[0] + n[1]; }
-    // code number e of the set, clamped into [0, kmax] (out-of-range e, or an empty set, gives a harmless code)
-    __device__ __forceinline__ int code(int e, int kmax) const {
-        e = max(0, min(e, total() - 1));
-        const int g = e >= n[0];
-        e -= g ? n[0] : 0;
-        const int pcg = max(pc[g], 1);
-        const int a = e / pcg, jj = e - a * pcg;
-        const uint32_t it = (r[g] >> (9 * a)) & IT_MASK;
-        const int k = (int)(it * 16u) + (int)(__fns(c[g], 0, jj + 1) & 15u);
-        return max(0, min(k, kmax));
-    }
-};
-
-// job = (tile slot, tile, stage); every role walks the same sequence.
-struct JobIter {
-    int n_local, nq, nslots, i, q, slot;  // i = local tile index
-    __device__ __forceinline__ JobIter(int n_local_, int nq_, int nslots_)
-        : n_local(n_local_), nq(nq_), nslots(nslots_), i(0), q(0), slot(0) {}
-    __device__ __forceinline__ bool valid() const { return i < n_local; }
-    __device__ __forceinline__ void next() {
-        // one slot: tile after tile.  two slots: pair p = (2p, 2p+1): for q: (slot0, q), (slot1, q)
-        if (nslots == 1) {
-            if (++q == nq) {
-                q = 0;
-                ++i;
-            }
-            return;
-        }
-        const int pair0 = i & ~1;
-        if (slot == 0 && pair0 + 1 < n_local) {
-            slot = 1;
-            i = pair0 + 1;
-        } else {
-            slot = 0;
-            i = pair0;
-            if (++q == nq) {
-                q = 0;
-                i = pair0 + 2;
-            }
-        }
-    }
-};
 
 template <bool kDebug>
 __global__ void __launch_bounds__(NUM_THREADS, 1)

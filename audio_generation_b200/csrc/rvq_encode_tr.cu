@@ -1,0 +1,792 @@
+// rvq_encode_tr.cu -- K1 (+K2 fused) for d <= 128: the residual-vector-quantization stage loop as ONE persistent
+// sm_100a kernel whose fp32 residual tile lives in TENSOR MEMORY for all stages.  Replaces the per-stage
+// {distance, argmin, gather, subtract, EMA statistics} loop of som_quantizer.ResidualQuantizer.forward
+// (called at /root/reference/networks/vae.py:315-318).
+//
+// Why a second kernel: the generic kernel (rvq_encode_tc.cu) keeps the residual in an L2-resident scratch and
+// streams the codebook once per tile, which costs ~450 KB of L2->SM traffic per 128-frame tile-stage at
+// d = 128 -- more than the ~43 B/cycle an SM gets from L2 allows at the target rate.  Here
+//   * TMEM columns [0, 256)   = two 128-column fp32 accumulators (128 codes per MMA, double buffered),
+//   * TMEM columns [256, 512) = the fp32 residual of the two 128-frame tiles in flight (d columns each);
+//     an update thread owns ONE frame (TMEM lane) and reads / rewrites its residual with tcgen05.ld / .st,
+//   * the selected fp32 code vectors, the frames x and the outputs xq move between global and shared memory
+//     as per-frame bulk copies (cp.async.bulk) through one padded staging buffer, so no LSU wavefront is spent
+//     on uncoalesced global accesses,
+//   * EMA sums leave as bulk reductions (cp.reduce.async.bulk .add.f32) of the staged residual rows.
+// What remains per tile-stage is the fp16 codebook stream (2 K d bytes) and the gathered code rows (512 d bytes).
+//
+// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 / 8-11 = scan groups 0 / 1 (accumulator buffers 0 / 1), warps 12-15 / 16-19 = update groups of
+// tile slots 0 / 1 (thread = frame).
+#include <cuda.h>
+#include <cstdlib>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "exact.cuh"
+#include "encode_common.cuh"
+
+namespace rvq {
+namespace tr {
+
+constexpr int CH = 128;  // codes per MMA / accumulator buffer
+constexpr int SCAN_WARP0 = 4;
+constexpr int SCAN_THREADS = 256;
+constexpr int UPD_WARP0 = 12;
+constexpr int GRP_THREADS = 128;  // one update group = 4 warps = the 128 TMEM lanes
+constexpr int NUM_THREADS = UPD_WARP0 * 32 + 2 * GRP_THREADS;  // 640
+constexpr int MAX_RING = 8;
+constexpr int MAX_NQ = 64;
+constexpr uint32_t B_STAGE_BYTES = CH * KSLICE * 2;  // 16 KiB
+constexpr uint32_t BAR_SCAN = 1;                     // named barrier of the 256 scan threads
+constexpr uint32_t BAR_GRP0 = 2;                     // + slot: named barrier of one update group
+constexpr uint32_t TMEM_RES_COL = 256;               // first residual column
+
+struct Params {
+    const float* x;
+    long long N;
+    RowAddrT ad;
+    int d, nq, K, Kpad, q_begin;
+    const float* cb;       // [*, K, d] fp32 master
+    const float* cb_norm;  // [*, Kpad] scaled norms
+    const float* cb_meta;  // [*, 8]
+    float* xq;
+    long long* idx;
+    double* commit_sq;
+    float* stats_sum;
+    float* stats_cnt;
+    int num_tiles, nstage, nslots, pitch;  // pitch: floats per staging row (d + 4)
+    uint32_t off_stg, off_B, off_misc;     // A tiles (one per slot) at offset 0
+    unsigned long long* prof;              // [16] cycle / event counters (RVQ_PROFILE=1) or null
+};
+
+struct __align__(16) Misc {
+    uint64_t full[MAX_RING], empty[MAX_RING], tmem_full[2], tmem_empty[2], norm_full[2], a_ready[2], scan_done[2];
+    uint64_t stg_full[2], stg_free;
+    alignas(16) float norms[2][CH];  // 16-byte aligned (bulk-copy destination); scaled ||c||^2 of the chunk in each accumulator buffer (bulk-copied)
+    uint32_t tmem_base;
+    float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
+    float grp_best[2][2][TILE_M];   // [job parity][scan group][frame]: best score the group saw
+    uint32_t g_rows[2][2][TILE_M];  // [slot][group][frame]: loads that may hold a candidate
+    uint16_t g_cols[2][2][TILE_M];  // [slot][group][frame]: columns that may hold a candidate
+    int win[2][TILE_M];             // [slot][frame]: selected code
+    int n_score[2], n_dirty[2];
+    uint8_t score_rows[2][TILE_M], dirty_rows[2][TILE_M];
+    uint16_t dirty_cols[2][TILE_M];
+    float red_s[2][4];
+    int red_k[2][4];
+    double commit_acc[MAX_NQ];
+};
+
+// 32 consecutive features of one frame -> fp16 operand (scaled by sa) in the UMMA A tile
+__device__ __forceinline__ void store_a32(uint8_t* a_tile, int row, int c0, const uint32_t (&v)[32], float sa) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        __half2 h;
+        h = __floats2half2_rn(__uint_as_float(v[j + 0]) * sa, __uint_as_float(v[j + 1]) * sa);
+        pk.x = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2half2_rn(__uint_as_float(v[j + 2]) * sa, __uint_as_float(v[j + 3]) * sa);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2half2_rn(__uint_as_float(v[j + 4]) * sa, __uint_as_float(v[j + 5]) * sa);
+        pk.z = *reinterpret_cast<const uint32_t*>(&h);
+        h = __floats2half2_rn(__uint_as_float(v[j + 6]) * sa, __uint_as_float(v[j + 7]) * sa);
+        pk.w = *reinterpret_cast<const uint32_t*>(&h);
+        *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, c0 + j)) = pk;
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_b = smem + p.off_B;
+    float* staging = reinterpret_cast<float*>(smem + p.off_stg);
+    Misc* misc = reinterpret_cast<Misc*>(smem + p.off_misc);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = p.d, nq = p.nq;
+    const int n_ks = d / KSLICE;
+    const int n_chunks = p.Kpad / CH;
+    const int nstage = p.nstage;
+    const uint32_t a_tile_bytes = (uint32_t)n_ks * A_SLICE_BYTES;
+    const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nslots = p.nslots;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nstage; ++i) {
+            mbar_init(&misc->full[i], 1);
+            mbar_init(&misc->empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&misc->tmem_full[i], 1);
+            mbar_init(&misc->tmem_empty[i], 4);  // one arrive per scan warp of the group
+            mbar_init(&misc->norm_full[i], 1);
+            mbar_init(&misc->a_ready[i], GRP_THREADS);
+            mbar_init(&misc->scan_done[i], SCAN_THREADS);
+            mbar_init(&misc->stg_full[i], GRP_THREADS);
+            misc->n_score[i] = 0;
+            misc->n_dirty[i] = 0;
+        }
+        mbar_init(&misc->stg_free, GRP_THREADS);
+        for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
+        fence_mbar_init();
+    }
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_b);
+    if (warp == 2) tmem_alloc<512>(&misc->tmem_base);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = misc->tmem_base;
+
+    // Register budget: 640 threads x 96 = 61440 registers at launch; setmaxnreg.inc can only take what
+    // setmaxnreg.dec released inside this CTA: 40*128 (control) + 88*256 (scan) + 128*256 (update) = 60416.
+    // setmaxnreg is warpgroup-aligned: one instruction per warpgroup, before its warps split into roles.
+    if (warp < SCAN_WARP0) {
+        reg_dealloc<40>();
+        if (warp == 0) {
+            // ======================================================= TMA producer (codebook slices)
+            if (lane == 0) {
+                uint32_t it = 0;
+                for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+                    const int row0 = (p.q_begin + job.q) * p.Kpad;
+                    for (int c = 0; c < n_chunks; ++c) {
+                        for (int ks = 0; ks < n_ks; ++ks, ++it) {
+                            const uint32_t s = it % nstage, ph = (it / nstage) & 1;
+                            mbar_wait(&misc->empty[s], ph ^ 1);
+                            mbar_arrive_expect_tx(&misc->full[s], B_STAGE_BYTES);
+                            tma_load_2d(smem_b + (size_t)s * B_STAGE_BYTES, &tmap_b, &misc->full[s], ks * KSLICE,
+                                        row0 + c * CH);
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ======================================================= MMA issuer
+            const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CH);
+            uint32_t it = 0, g = 0, aphase = 0;
+            for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+                const int sl = job.slot % nslots;
+                mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);
+                aphase ^= 1u << sl;
+                tc_fence_after_sync();
+                const uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const uint32_t buf = g & 1, use = g >> 1;
+                    mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
+                    tc_fence_after_sync();
+                    if (lane == 0) {
+                        // the scan group has released this buffer: its norm slice can be replaced as well
+                        mbar_arrive_expect_tx(&misc->norm_full[buf], CH * 4);
+                        bulk_load_1d(misc->norms[buf], p.cb_norm + (size_t)(p.q_begin + job.q) * p.Kpad + c * CH, CH * 4,
+                                     &misc->norm_full[buf]);
+                    }
+                    const uint32_t tmem_d = tmem_base + buf * CH;
+                    for (int ks = 0; ks < n_ks; ++ks, ++it) {
+                        const uint32_t s = it % nstage, ph = (it / nstage) & 1;
+                        mbar_wait(&misc->full[s], ph);
+                        tc_fence_after_sync();
+                        if (lane == 0) {
+                            const uint64_t adesc = umma_desc_sw128(smem_u32(a_tile + (size_t)ks * A_SLICE_BYTES));
+                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)s * B_STAGE_BYTES));
+#pragma unroll
+                            for (int k16 = 0; k16 < KSLICE / 16; ++k16) {
+                                // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
+                                umma_f16_ss(tmem_d, adesc + (uint64_t)(k16 * 2), bdesc + (uint64_t)(k16 * 2), idesc,
+                                            (ks | k16) != 0);
+                            }
+                            umma_commit(&misc->empty[s]);  // frees the ring slot when these MMAs retire
+                            if (ks == n_ks - 1) umma_commit(&misc->tmem_full[buf]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp < UPD_WARP0) {
+        reg_dealloc<88>();
+        // =========================================================== scan groups (argmin epilogue)
+        const int e = threadIdx.x - SCAN_WARP0 * 32;  // 0..255
+        const int grp = e >> 7;                       // scan group = accumulator buffer
+        const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
+        uint32_t g = 0, aphase = 0, jpar = 0;
+        long long t_scan = 0, t_wait = 0, t_full = 0;
+        for (JobIter job(n_local, nq, nslots); job.valid(); job.next(), jpar ^= 1u) {
+            const int sl = job.slot % nslots;
+            long long t0 = clock64();
+            mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);  // row constants of this job are visible
+            aphase ^= 1u << sl;
+            const float na = misc->row_na[sl][my_row];
+            const float delta = misc->row_delta[sl][my_row];
+            float Cm[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) Cm[j] = BIG;
+            float m1 = BIG, m2 = BIG, m3 = BIG, m4 = BIG;
+            long long t1 = clock64();
+            t_wait += t1 - t0;
+            for (int c = 0; c < n_chunks; ++c, ++g) {
+                if ((int)(g & 1) != grp) continue;
+                const long long tw0 = clock64();
+                mbar_wait(&misc->tmem_full[grp], (g >> 1) & 1);
+                mbar_wait(&misc->norm_full[grp], (g >> 1) & 1);
+                tc_fence_after_sync();
+                t_full += clock64() - tw0;
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CH;
+                const float* nptr = misc->norms[grp];
+                uint32_t va[16], vb[16];
+                tmem_ld_32x16(taddr, va);
+                uint32_t it = (uint32_t)c * (CH / 16);
+#pragma unroll 1
+                for (int cb = 0; cb < CH; cb += 32, it += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_32x16(taddr + cb + 16, vb);
+                    scan16_2d(va, nptr + cb, na, it, Cm, m1, m2, m3, m4, nullptr);
+                    tmem_ld_wait();
+                    if (cb + 32 < CH) tmem_ld_32x16(taddr + cb + 32, va);
+                    scan16_2d(vb, nptr + cb + 16, na, it + 1, Cm, m1, m2, m3, m4, nullptr);
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&misc->tmem_empty[grp]);
+            }
+            // ---------------- stage end: exchange the groups' best scores, list this group's candidates
+            float vb_ = fminf(fminf(Cm[0], Cm[1]), Cm[2]);
+#pragma unroll
+            for (int j = 3; j < 15; j += 2) vb_ = fminf(fminf(vb_, Cm[j]), Cm[j + 1]);
+            vb_ = fminf(vb_, Cm[15]);
+            misc->grp_best[jpar][grp][my_row] = vb_;
+            named_bar_sync(BAR_SCAN, SCAN_THREADS);
+            {
+                const float best = fminf(vb_, misc->grp_best[jpar][grp ^ 1][my_row]);
+                // Certificate: a code can be the exact argmin only if its approximate score is <= T.
+                const float T = best + delta;
+                // load minima carry `it` in their low 9 mantissa bits: |packed - r| <= 2^-14 |r|, and every load
+                // minimum r of interest lies in [best, T], so |r| <= |best| + delta
+                const float T2 = T + (fabsf(best) + 2.f * delta) * 1.220703125e-4f;
+                // NaN / overflow / forced exact (no usable filter result), or more than three loads in reach
+                const bool nofilter = !(best < BIG) || !(T2 < BIG);
+                const bool over = nofilter || (m4 <= T2);
+                const uint32_t nr = (uint32_t)(m1 <= T2) + (uint32_t)(m2 <= T2) + (uint32_t)(m3 <= T2);
+                uint32_t cols = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cols |= (Cm[j] <= T) ? (1u << j) : 0u;
+                if (nofilter) cols = 0xFFFFu;
+                const uint32_t rows = (__float_as_uint(m1) & IT_MASK) | ((__float_as_uint(m2) & IT_MASK) << 9) |
+                                      ((__float_as_uint(m3) & IT_MASK) << 18) | (nr << 27) | (over ? G_OVER : 0u);
+                misc->g_rows[sl][grp][my_row] = rows;
+                misc->g_cols[sl][grp][my_row] = (uint16_t)cols;
+            }
+            mbar_arrive(&misc->scan_done[sl]);
+            t_scan += clock64() - t1;
+        }
+        if (p.prof && e == 0) {
+            atomicAdd(p.prof + 0, (unsigned long long)t_scan);
+            atomicAdd(p.prof + 1, (unsigned long long)t_wait);
+            atomicAdd(p.prof + 11, (unsigned long long)t_full);
+        }
+    } else {
+        reg_alloc<128>();
+        // =========================================================== update groups (thread = frame)
+        const int s = (warp - UPD_WARP0) >> 2;    // tile slot served by this group
+        const int row = (warp & 3) * 32 + lane;   // frame of the tile = TMEM lane (UPD_WARP0 % 4 == 0)
+        const int gw = warp & 3;                  // warp inside the group
+        if (s < nslots) {
+            const uint32_t t_r = tmem_base + ((uint32_t)(gw * 32) << 16) + TMEM_RES_COL + (uint32_t)(s * d);
+            float* stg_row = staging + (size_t)row * p.pitch;
+            uint8_t* a_tile = smem + (size_t)s * a_tile_bytes;
+            const bool row_major = (p.ad.sd == 1);
+            const uint32_t bar_grp = BAR_GRP0 + (uint32_t)s;
+            const uint32_t row_bytes = (uint32_t)d * 4u;
+            uint32_t stg_par = 0, sphase = 0;
+            long long t_upd = 0, t_wait = 0, t_rank = 0, t_gather = 0, t_apply = 0, t_tail = 0, t_acq = 0;
+            unsigned long long n_dirty_tot = 0, n_multi_tot = 0, n_jobs = 0;
+
+            // the staging buffer is handed from critical section to critical section in one global order:
+            // prologue of slot 0, prologue of slot 1, then the jobs in JobIter order
+            auto acquire = [&](int ticket) {
+                if (ticket > 0) mbar_wait(&misc->stg_free, (uint32_t)(ticket - 1) & 1u);
+            };
+            auto release = [&]() { mbar_arrive(&misc->stg_free); };
+            auto wait_staging = [&]() {
+                mbar_wait(&misc->stg_full[s], stg_par);
+                stg_par ^= 1u;
+            };
+
+            // load tile `tile` into this slot (staging held): residual <- x, fp16 operand + row constants of stage 0
+            auto load_tile = [&](int tile) {
+                const long long n = (long long)tile * TILE_M + row;
+                const bool valid = n < p.N;
+                const long long off = valid ? p.ad.row(n) : 0;
+                if (row_major) {
+                    if (valid) {
+                        mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
+                        bulk_load_1d(stg_row, p.x + off, row_bytes, &misc->stg_full[s]);
+                    } else {
+                        mbar_arrive(&misc->stg_full[s]);
+                    }
+                    wait_staging();
+                }
+                float sq = 0.f, amax = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < d; c0 += 32) {
+                    uint32_t v[32];
+                    if (row_major) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (valid) t = *reinterpret_cast<const float4*>(stg_row + c0 + j);
+                            v[j + 0] = __float_as_uint(t.x);
+                            v[j + 1] = __float_as_uint(t.y);
+                            v[j + 2] = __float_as_uint(t.z);
+                            v[j + 3] = __float_as_uint(t.w);
+                        }
+                    } else {
+                        // frames-fastest storage (the reference's (B, d, L) tensor): lanes = consecutive frames
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = valid ? __float_as_uint(p.x[off + (long long)(c0 + j) * p.ad.sd]) : 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float f = __uint_as_float(v[j]);
+                        sq = fmaf(f, f, sq);
+                        amax = fmaxf(amax, fabsf(f));
+                    }
+                    tmem_st_32x32(t_r + c0, v);
+                }
+                tmem_st_wait();
+                const float* mq = p.cb_meta + (size_t)p.q_begin * META_STRIDE;
+                const float sb = mq[0], cnmax = mq[1];
+                const int b = ilog2f_floor(sb);
+                bool force_exact = !isfinite(sq);
+                const int a = pick_row_exp(amax, b, force_exact);
+                const float sa = exp2i(a);
+#pragma unroll 1
+                for (int c0 = 0; c0 < d; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_r + c0, v);
+                    tmem_ld_wait();
+                    store_a32(a_tile, row, c0, v, sa);
+                }
+                float na, delta;
+                row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
+                misc->row_amax[s][row] = amax;
+                misc->row_na[s][row] = na;
+                misc->row_delta[s][row] = delta;
+                fence_proxy_async_smem();
+            };
+
+            int ticket = 0;
+            // ---------------- prologue: first tile of each slot
+            for (int ps = 0; ps < nslots && ps < n_local; ++ps, ++ticket) {
+                if (ps != s) continue;
+                acquire(ticket);
+                load_tile(blockIdx.x + ps * gridDim.x);
+                release();
+                mbar_arrive(&misc->a_ready[s]);
+            }
+            for (JobIter job(n_local, nq, nslots); job.valid(); job.next(), ++ticket) {
+                if (job.slot % nslots != s) continue;
+                const int q = job.q, q_abs = p.q_begin + q;
+                const int tile = blockIdx.x + job.i * gridDim.x;
+                const long long n = (long long)tile * TILE_M + row;
+                const bool valid = n < p.N;
+                const int next_q_abs = (q + 1 < nq) ? q_abs + 1 : -1;
+                const float* cbq = p.cb + (size_t)q_abs * p.K * d;
+                const int Kv = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
+                const long long tj0 = clock64();
+                mbar_wait(&misc->scan_done[s], sphase);
+                sphase ^= 1u;
+                const long long tj1 = clock64();
+                // ---------------- classify my frame: certified (one candidate), several candidates, exact scan
+                const uint32_t r0 = misc->g_rows[s][0][row], r1 = misc->g_rows[s][1][row];
+                const uint32_t c0m = misc->g_cols[s][0][row], c1m = misc->g_cols[s][1][row];
+                const int n0 = (int)((r0 >> 27) & 3u) * __popc(c0m), n1 = (int)((r1 >> 27) & 3u) * __popc(c1m);
+                int w = 0;
+                bool special = false;
+                if (((r0 | r1) & G_OVER) || n0 + n1 == 0) {
+                    const int pos = atomicAdd(&misc->n_dirty[s], 1);
+                    misc->dirty_rows[s][pos] = (uint8_t)row;
+                    misc->dirty_cols[s][pos] = (uint16_t)((c0m | c1m) ? (c0m | c1m) : 0xFFFFu);
+                    special = true;
+                } else if (n0 + n1 == 1) {
+                    w = n0 ? (int)((r0 & IT_MASK) * 16u) + __ffs(c0m) - 1 : (int)((r1 & IT_MASK) * 16u) + __ffs(c1m) - 1;
+                    w = max(0, min(w, Kv - 1));  // cannot bind (padding codes score 2^100); keeps the gather in bounds
+                } else {
+                    misc->score_rows[s][atomicAdd(&misc->n_score[s], 1)] = (uint8_t)row;
+                    special = true;
+                }
+                acquire(ticket);
+                const long long tj2 = clock64();
+                if (!special) {
+                    mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
+                    bulk_load_1d(stg_row, cbq + (size_t)w * d, row_bytes, &misc->stg_full[s]);
+                }
+                // frames that need exact scores expose their residual row in the staging buffer
+                if (__any_sync(0xffffffffu, special)) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < d; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_r + c0, v);
+                        tmem_ld_wait();
+                        if (special) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<uint4*>(stg_row + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    }
+                }
+                named_bar_sync(bar_grp, GRP_THREADS);
+                // ---------------- exact re-rank (8 lanes per frame, 16 frames per pass)
+                const int n_score = misc->n_score[s], n_dirty = misc->n_dirty[s];
+                {
+                    const int sub = lane & 7, slot16 = (gw * 32 + lane) >> 3;
+#pragma unroll 1
+                    for (int base = 0; base < n_score; base += GRP_THREADS / 8) {
+                        const int i = base + slot16;
+                        const bool sc = i < n_score;
+                        const int rr = misc->score_rows[s][sc ? i : 0];
+                        const CandSet cs(misc->g_rows[s][0][rr], misc->g_cols[s][0][rr], misc->g_rows[s][1][rr],
+                                         misc->g_cols[s][1][rr]);
+                        const int nc = sc ? cs.total() : 0;
+                        int nc_max = nc;  // the whole warp walks the longest list of its four frames
+                        nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, 8));
+                        nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, 16));
+                        const float* rrow = staging + (size_t)rr * p.pitch;
+                        float bs = __int_as_float(0x7f800000);
+                        int kwin = 0x7fffffff;
+#pragma unroll 1
+                        for (int j = 0; j < nc_max; j += 2) {
+                            const int k1 = cs.code(j, Kv - 1), k2 = cs.code(j + 1, Kv - 1);
+                            const float* cc[2] = {cbq + (size_t)k1 * d, cbq + (size_t)k2 * d};
+                            float sv[2];
+                            exact_score8_n<2>(rrow, cc, d, sub, sv);
+                            if (better(sv[0], k1, bs, kwin)) {
+                                bs = sv[0];
+                                kwin = k1;
+                            }
+                            if (better(sv[1], k2, bs, kwin)) {
+                                bs = sv[1];
+                                kwin = k2;
+                            }
+                        }
+                        if (sc && sub == 0) misc->win[s][rr] = kwin;
+                    }
+                }
+                // ---------------- frames the filter could not bound: exact scan of the columns in reach
+#pragma unroll 1
+                for (int i = 0; i < n_dirty; ++i) {
+                    const int rr = misc->dirty_rows[s][i];
+                    const uint32_t cols = misc->dirty_cols[s][i];
+                    const int n_it = (Kv + 15) / 16, per_w = (n_it + 3) / 4;
+                    const int it0 = min(n_it, gw * per_w), it1 = min(n_it, it0 + per_w);
+                    const ScoreIdx bsc = exact_scan_cols(staging + (size_t)rr * p.pitch, cbq, d, it0, it1, cols, Kv, lane);
+                    if (lane == 0) {
+                        misc->red_s[s][gw] = bsc.s;
+                        misc->red_k[s][gw] = bsc.k;
+                    }
+                    named_bar_sync(bar_grp, GRP_THREADS);
+                    if (gw == 0 && lane == 0) {
+                        float bs = misc->red_s[s][0];
+                        int bk = misc->red_k[s][0];
+                        for (int ww = 1; ww < 4; ++ww)
+                            if (better(misc->red_s[s][ww], misc->red_k[s][ww], bs, bk)) {
+                                bs = misc->red_s[s][ww];
+                                bk = misc->red_k[s][ww];
+                            }
+                        if (bk < 0 || bk >= Kv) bk = 0;
+                        misc->win[s][rr] = bk;
+                    }
+                    named_bar_sync(bar_grp, GRP_THREADS);
+                }
+                named_bar_sync(bar_grp, GRP_THREADS);  // winners visible; residual rows in staging no longer read
+                if (gw == 0 && lane == 0) {
+                    misc->n_score[s] = 0;
+                    misc->n_dirty[s] = 0;
+                }
+                if (special) {
+                    w = misc->win[s][row];
+                    fence_proxy_async_smem();  // my generic-proxy writes of this staging row precede the bulk copy
+                    mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
+                    bulk_load_1d(stg_row, cbq + (size_t)w * d, row_bytes, &misc->stg_full[s]);
+                }
+                const long long tj3 = clock64();
+                // ---------------- constants of the next stage's operand (scale chosen from a bound known now)
+                const bool write_a = next_q_abs >= 0;
+                float sb = 1.f, cnmax = 0.f, sa = 0.f;
+                int a = 0, b = 0;
+                bool force_exact = false;
+                if (write_a) {
+                    const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
+                    sb = mq[0];
+                    cnmax = mq[1];
+                    b = ilog2f_floor(sb);
+                    a = pick_row_exp(misc->row_amax[s][row] + p.cb_meta[(size_t)q_abs * META_STRIDE + 2], b, force_exact);
+                    sa = exp2i(a);
+                }
+                if (valid) {
+                    p.idx[n * nq + q] = w;
+                    if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + w, 1.f);
+                }
+                const bool stats = p.stats_sum != nullptr;
+                wait_staging();  // the selected code vectors have landed
+                const long long tj4 = clock64();
+                // ---------------- r <- r - c (fp32, tensor memory), next operand row, statistics row
+                float sq = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < d; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_r + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 cv = *reinterpret_cast<const float4*>(stg_row + c0 + j);
+                        // the staging row becomes the stage INPUT residual (source of the EMA bulk reduction)
+                        if (stats) *reinterpret_cast<uint4*>(stg_row + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        const float n0f = __uint_as_float(v[j + 0]) - cv.x;
+                        const float n1f = __uint_as_float(v[j + 1]) - cv.y;
+                        const float n2f = __uint_as_float(v[j + 2]) - cv.z;
+                        const float n3f = __uint_as_float(v[j + 3]) - cv.w;
+                        sq = fmaf(n0f, n0f, sq);
+                        sq = fmaf(n1f, n1f, sq);
+                        sq = fmaf(n2f, n2f, sq);
+                        sq = fmaf(n3f, n3f, sq);
+                        v[j + 0] = __float_as_uint(n0f);
+                        v[j + 1] = __float_as_uint(n1f);
+                        v[j + 2] = __float_as_uint(n2f);
+                        v[j + 3] = __float_as_uint(n3f);
+                    }
+                    tmem_st_32x32(t_r + c0, v);
+                    if (write_a) store_a32(a_tile, row, c0, v, sa);
+                }
+                if (stats) {
+                    fence_proxy_async_smem();
+                    if (valid) {
+                        bulk_reduce_add_f32(p.stats_sum + ((size_t)q_abs * p.K + w) * d, stg_row, row_bytes);
+                        bulk_commit();
+                    }
+                }
+                tmem_st_wait();
+                misc->row_amax[s][row] = sqrtf(sq) * 1.00002f;  // ||r'||_2 >= max|r'|
+                if (write_a) {
+                    if (!isfinite(sq)) force_exact = true;
+                    float na, delta;
+                    row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
+                    misc->row_na[s][row] = na;
+                    misc->row_delta[s][row] = delta;
+                }
+                {
+                    // commit-loss partial: sum over the valid frames of this warp
+                    double cs = valid ? (double)sq : 0.0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+                    if (lane == 0 && cs != 0.0) atomicAdd(&misc->commit_acc[q], cs);
+                }
+                if (stats && valid) bulk_wait_read0();  // the reduction has read my staging row
+                const long long tj5 = clock64();
+                if (write_a) {
+                    fence_proxy_async_smem();
+                    release();
+                    mbar_arrive(&misc->a_ready[s]);
+                } else {
+                    // ---------------- last stage: xq = x - final residual, then the slot takes its next tile
+                    const long long off = valid ? p.ad.row(n) : 0;
+                    if (row_major) {
+                        if (valid) {
+                            mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
+                            bulk_load_1d(stg_row, p.x + off, row_bytes, &misc->stg_full[s]);
+                        } else {
+                            mbar_arrive(&misc->stg_full[s]);
+                        }
+                        wait_staging();
+                    }
+#pragma unroll 1
+                    for (int c0 = 0; c0 < d; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(t_r + c0, v);
+                        tmem_ld_wait();
+                        if (row_major) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                float4 xv = *reinterpret_cast<const float4*>(stg_row + c0 + j);
+                                xv.x -= __uint_as_float(v[j + 0]);
+                                xv.y -= __uint_as_float(v[j + 1]);
+                                xv.z -= __uint_as_float(v[j + 2]);
+                                xv.w -= __uint_as_float(v[j + 3]);
+                                *reinterpret_cast<float4*>(stg_row + c0 + j) = xv;
+                            }
+                        } else if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const long long o = off + (long long)(c0 + j) * p.ad.sd;
+                                p.xq[o] = p.x[o] - __uint_as_float(v[j]);
+                            }
+                        }
+                    }
+                    if (row_major) {
+                        fence_proxy_async_smem();
+                        if (valid) {
+                            bulk_store_1d(p.xq + off, stg_row, row_bytes);
+                            bulk_commit();
+                            bulk_wait_read0();
+                        }
+                    }
+                    const int next_i = job.i + nslots;
+                    if (next_i < n_local) {
+                        load_tile(blockIdx.x + next_i * gridDim.x);
+                        release();
+                        mbar_arrive(&misc->a_ready[s]);
+                    } else {
+                        fence_proxy_async_smem();
+                        release();
+                    }
+                }
+                const long long tj6 = clock64();
+                t_wait += tj1 - tj0;
+                t_acq += tj2 - tj1;
+                t_rank += tj3 - tj2;
+                t_gather += tj4 - tj3;
+                t_apply += tj5 - tj4;
+                t_tail += tj6 - tj5;
+                t_upd += tj6 - tj1;
+                n_dirty_tot += n_dirty;
+                n_multi_tot += n_score;
+                ++n_jobs;
+            }
+            bulk_wait0();  // my bulk stores / reductions are complete before the kernel ends
+            if (p.prof && gw == 0 && lane == 0) {
+                atomicAdd(p.prof + 2, (unsigned long long)t_upd);
+                atomicAdd(p.prof + 3, (unsigned long long)t_acq);
+                atomicAdd(p.prof + 4, n_dirty_tot);
+                atomicAdd(p.prof + 5, n_jobs);
+                atomicAdd(p.prof + 6, n_multi_tot);
+                atomicAdd(p.prof + 7, (unsigned long long)t_wait);
+                atomicAdd(p.prof + 8, (unsigned long long)t_rank);
+                atomicAdd(p.prof + 9, (unsigned long long)t_apply);
+                atomicAdd(p.prof + 10, (unsigned long long)t_gather);
+                atomicAdd(p.prof + 12, (unsigned long long)t_tail);
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < nq) {
+        const double v = misc->commit_acc[threadIdx.x];
+        if (v != 0.0) atomicAdd(p.commit_sq + threadIdx.x, v);
+    }
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace tr
+}  // namespace rvq
+
+// ------------------------------------------------------------------------------------------ host side
+using namespace rvq;
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled_tr() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+}  // namespace
+
+// d in {64, 128}: both tiles' residuals fit in TMEM columns [256, 512)
+bool rvq_tr_supported(int d) { return d == 64 || d == 128; }
+
+int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d, int nq,
+                  int K, int q_begin, const float* cb, const void* cb_op, int nq_total, const float* cb_norm,
+                  const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
+                  float* stats_cnt, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (K > 32 * CHUNK_N) {
+        set_error("rvq_encode: at most %d codes per stage are supported (got %d)", 32 * CHUNK_N, K);
+        return RVQ_ERR_ARG;
+    }
+    if (nq > tr::MAX_NQ) {
+        set_error("rvq_encode: at most %d stages are supported (got %d)", tr::MAX_NQ, nq);
+        return RVQ_ERR_ARG;
+    }
+    int dev = 0, num_sms = 0, smem_max = 0;
+    RVQ_CUDA(cudaGetDevice(&dev));
+    RVQ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    RVQ_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int Kpad = round_up(K, CHUNK_N);
+    tr::Params p{};
+    p.nslots = 2;
+    p.pitch = d + 4;
+    const uint32_t a_bytes = (uint32_t)(d / KSLICE) * A_SLICE_BYTES;
+    const uint32_t stg_bytes = (uint32_t)((TILE_M * p.pitch * 4 + 1023) / 1024 * 1024);
+    const uint32_t misc_bytes = (uint32_t)((sizeof(tr::Misc) + 1023) / 1024 * 1024);
+    p.off_stg = (uint32_t)p.nslots * a_bytes;
+    p.off_B = p.off_stg + stg_bytes;
+    const uint32_t fixed = p.off_B + misc_bytes + 1024;
+    int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / tr::B_STAGE_BYTES) : 0;
+    if (ns > tr::MAX_RING) ns = tr::MAX_RING;
+    if (ns < 2) {
+        set_error("rvq_encode: d=%d leaves no room for the codebook ring in %d bytes of shared memory", d, smem_max);
+        return RVQ_ERR_ARG;
+    }
+    p.nstage = ns;
+    p.off_misc = p.off_B + (uint32_t)ns * tr::B_STAGE_BYTES;
+    const uint32_t smem_total = p.off_misc + misc_bytes + 1024;
+
+    EncodeTiledFn encode = get_encode_tiled_tr();
+    if (!encode) {
+        set_error("rvq_encode: cuTensorMapEncodeTiled is not available from the driver");
+        return RVQ_ERR_CUDA;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nq_total * Kpad};
+    const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)tr::CH};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(cb_op), gdim, gstride, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("rvq_encode: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        return RVQ_ERR_CUDA;
+    }
+    const int num_tiles = (int)((N + TILE_M - 1) / TILE_M);
+    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+    p.x = x;
+    p.N = N;
+    p.ad = RowAddrT{L, sb, sl, sd};
+    p.d = d;
+    p.nq = nq;
+    p.K = K;
+    p.Kpad = Kpad;
+    p.q_begin = q_begin;
+    p.cb = cb;
+    p.cb_norm = cb_norm;
+    p.cb_meta = cb_meta;
+    p.xq = xq;
+    p.idx = idx;
+    p.commit_sq = commit_sq;
+    p.stats_sum = stats_sum;
+    p.stats_cnt = stats_cnt;
+    p.num_tiles = num_tiles;
+    static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
+    if (want_prof && ws && ws_bytes >= 128) {
+        // counters live in the LAST 128 bytes of the workspace
+        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 128) & ~(size_t)7));
+        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 128, st));
+    }
+    RVQ_CUDA(cudaFuncSetAttribute(tr::rvq_encode_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
+    tr::rvq_encode_tr_kernel<<<grid, tr::NUM_THREADS, smem_total, st>>>(tmap, p);
+    RVQ_CUDA(cudaGetLastError());
+    return RVQ_OK;
+}

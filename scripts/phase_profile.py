@@ -39,6 +39,12 @@ ctas = min(148, (N + 127) // 128)
 cyc_total = ms * 1e-3 * 1.965e9 * ctas / n
 print(f"workload {name} update={upd} after {nsteps} steps N={N} ms={ms:.3f} tile-stages={prof[5]}  wall cycles per tile-stage per CTA ~{cyc_total:.0f} "
       f"(MMA floor {K * d * 128 // 4096})")
+if d <= 128 and os.environ.get("RVQ_KERNEL") != "tc":
+    print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+a_ready wait {prof[1]/n:.0f}, of scan: tmem_full wait {prof[11]/n:.0f})")
+    print(f"  update group (per job): total={prof[2]/n:.0f} (+scan_done wait {prof[7]/n:.0f})  staging-acquire={prof[3]/n:.0f} "
+          f"rerank={prof[8]/n:.0f} gather-wait={prof[10]/n:.0f} apply={prof[9]/n:.0f} tail={prof[12]/n:.0f}")
+    print(f"dirty rows per tile-stage={prof[4]/n:.3f}  multi-candidate rows per tile-stage={prof[6]/n:.2f}")
+    sys.exit(0)
 print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+wait {prof[1]/n:.0f})  update={prof[2]/n:.0f} "
       f"dirty={prof[3]/n:.0f} (+wait {prof[7]/n:.0f})")
 print(f"  scan: of which waiting for the accumulator (tmem_full) = {prof[11]/n:.0f}")
