@@ -126,9 +126,19 @@ struct CandSet {
         const int g = e >= n[0];
         e -= g ? n[0] : 0;
         const int pcg = max(pc[g], 1);
-        const int a = e / pcg, jj = e - a * pcg;
+        int a = 0;  // at most three loads per group
+        if (e >= pcg) {
+            e -= pcg;
+            a = 1;
+        }
+        if (e >= pcg) {
+            e -= pcg;
+            a = 2;
+        }
+        uint32_t m = c[g];
+        for (int i = 0; i < e && i < 15; ++i) m &= m - 1;  // drop the e lowest set bits
         const uint32_t it = (r[g] >> (9 * a)) & IT_MASK;
-        const int k = (int)(it * 16u) + (int)(__fns(c[g], 0, jj + 1) & 15u);
+        const int k = (int)(it * 16u) + ((__ffs(m) - 1) & 15);
         return max(0, min(k, kmax));
     }
 };

@@ -73,6 +73,54 @@ __device__ __forceinline__ void exact_score8_n(const float* r, const float* cons
     }
 }
 
+// NC independent (row, code) pairs scored together by one 8-lane group: the code loads of all pairs (global,
+// long latency) are in flight at once, the rows come from shared memory piece by piece.  Per pair the
+// arithmetic is exact_score8_n's (same fmaf chain, same butterfly), hence bit-identical scores.
+template <int NC, int NP>
+__device__ __forceinline__ void exact_seg_pairs(const float* const* r, const float* const* c, int p0, float* dot,
+                                                float* nrm) {
+    float4 cv[NC][NP];
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) cv[j][i] = ldg_nc_v4(c[j] + p0 + i * 32);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+            const float4 rv = *reinterpret_cast<const float4*>(r[j] + p0 + i * 32);
+            dot[j] = fmaf(rv.x, cv[j][i].x, dot[j]);
+            dot[j] = fmaf(rv.y, cv[j][i].y, dot[j]);
+            dot[j] = fmaf(rv.z, cv[j][i].z, dot[j]);
+            dot[j] = fmaf(rv.w, cv[j][i].w, dot[j]);
+            nrm[j] = fmaf(cv[j][i].x, cv[j][i].x, nrm[j]);
+            nrm[j] = fmaf(cv[j][i].y, cv[j][i].y, nrm[j]);
+            nrm[j] = fmaf(cv[j][i].z, cv[j][i].z, nrm[j]);
+            nrm[j] = fmaf(cv[j][i].w, cv[j][i].w, nrm[j]);
+        }
+    }
+}
+template <int NC>
+__device__ __forceinline__ void exact_score8_pairs(const float* const* r, const float* const* c, int d, int sub,
+                                                   float* out) {
+    float dot[NC], nrm[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) dot[j] = nrm[j] = 0.f;
+    int p0 = sub * 4;
+#pragma unroll 1
+    for (; p0 + 128 <= d + sub * 4; p0 += 128) exact_seg_pairs<NC, 4>(r, c, p0, dot, nrm);
+    if (d & 64) exact_seg_pairs<NC, 2>(r, c, p0, dot, nrm);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            dot[j] += __shfl_xor_sync(0xffffffffu, dot[j], o);
+            nrm[j] += __shfl_xor_sync(0xffffffffu, nrm[j], o);
+        }
+        out[j] = fmaf(-2.f, dot[j], nrm[j]);
+    }
+}
+
 __device__ __forceinline__ float exact_score8(const float* r, const float* __restrict__ c, int d,
                                               int sub) {
     const float* const cc[1] = {c};

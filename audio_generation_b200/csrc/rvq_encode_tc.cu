@@ -894,10 +894,10 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     p.dbg_scores = dbg_scores;
     p.dbg_rowscale = dbg_rowscale;
     static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
-    if (want_prof && ws && ws_bytes >= 128) {
-        // counters live in the LAST 128 bytes of the workspace
-        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 128) & ~(size_t)7));
-        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 128, st));
+    if (want_prof && ws && ws_bytes >= 256) {
+        // 32 counters live in the LAST 256 bytes of the workspace
+        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 256) & ~(size_t)7));
+        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 256, st));
     }
     {
         const size_t need = (size_t)grid * 2 * TILE_M * d * sizeof(float);

@@ -41,6 +41,8 @@ constexpr uint32_t B_STAGE_BYTES = CH * KSLICE * 2;  // 16 KiB
 constexpr uint32_t BAR_SCAN = 1;                     // named barrier of the 256 scan threads
 constexpr uint32_t BAR_GRP0 = 2;                     // + slot: named barrier of one update group
 constexpr uint32_t TMEM_RES_COL = 256;               // first residual column
+constexpr int MAX_PAIRS = 128;  // (frame, candidate) pairs one re-rank round can score
+constexpr int RS_ROWS = 16;  // residual rows one update group can expose per re-rank round (8 lanes per frame)
 
 struct Params {
     const float* x;
@@ -56,7 +58,8 @@ struct Params {
     float* stats_sum;
     float* stats_cnt;
     int num_tiles, nstage, nslots, pitch;  // pitch: floats per staging row (d + 4)
-    uint32_t off_stg, off_B, off_misc;     // A tiles (one per slot) at offset 0
+    int cluster;                           // CTAs per cluster sharing the codebook stream (TMA multicast)
+    uint32_t off_stg, off_rs, off_B, off_misc;  // A tiles (one per slot) at offset 0
     unsigned long long* prof;              // [16] cycle / event counters (RVQ_PROFILE=1) or null
 };
 
@@ -70,9 +73,10 @@ struct __align__(16) Misc {
     uint32_t g_rows[2][2][TILE_M];  // [slot][group][frame]: loads that may hold a candidate
     uint16_t g_cols[2][2][TILE_M];  // [slot][group][frame]: columns that may hold a candidate
     int win[2][TILE_M];             // [slot][frame]: selected code
-    int n_score[2], n_dirty[2];
-    uint8_t score_rows[2][TILE_M], dirty_rows[2][TILE_M];
-    uint16_t dirty_cols[2][TILE_M];
+    int n_special[2], n_pairs[2];
+    uint32_t pairs[2][MAX_PAIRS];     // [slot][i]: (exposed row slot << 16) | code
+    float pair_score[2][MAX_PAIRS];
+    uint8_t special_rows[2][TILE_M];  // [slot][i]: frame | 0x80 if it needs the exact scan
     float red_s[2][4];
     int red_k[2][4];
     double commit_acc[MAX_NQ];
@@ -101,6 +105,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_b = smem + p.off_B;
     float* staging = reinterpret_cast<float*>(smem + p.off_stg);
+    float* rstage_all = reinterpret_cast<float*>(smem + p.off_rs);
     Misc* misc = reinterpret_cast<Misc*>(smem + p.off_misc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,13 +114,17 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
     const int n_chunks = p.Kpad / CH;
     const int nstage = p.nstage;
     const uint32_t a_tile_bytes = (uint32_t)n_ks * A_SLICE_BYTES;
-    const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // every CTA of a cluster walks the same job sequence (tiles past the end are empty: all frames invalid)
+    const int n_local = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int CL = p.cluster;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
     const int nslots = p.nslots;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < nstage; ++i) {
             mbar_init(&misc->full[i], 1);
-            mbar_init(&misc->empty[i], 1);
+            mbar_init(&misc->empty[i], (uint32_t)CL);  // one tcgen05.commit arrive per CTA of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&misc->tmem_full[i], 1);
@@ -124,8 +133,8 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             mbar_init(&misc->a_ready[i], GRP_THREADS);
             mbar_init(&misc->scan_done[i], SCAN_THREADS);
             mbar_init(&misc->stg_full[i], GRP_THREADS);
-            misc->n_score[i] = 0;
-            misc->n_dirty[i] = 0;
+            misc->n_special[i] = 0;
+            misc->n_pairs[i] = 0;
         }
         mbar_init(&misc->stg_free, GRP_THREADS);
         for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
@@ -135,6 +144,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
     if (warp == 2) tmem_alloc<512>(&misc->tmem_base);
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // the peers' barriers are initialised before anything is multicast to them
     tc_fence_after_sync();
     const uint32_t tmem_base = misc->tmem_base;
 
@@ -147,32 +157,47 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             // ======================================================= TMA producer (codebook slices)
             if (lane == 0) {
                 uint32_t it = 0;
+                long long t_empty = 0;
+                const uint32_t part_bytes = B_STAGE_BYTES / (uint32_t)CL;
+                const int part_rows = CH / CL;
                 for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
                     const int row0 = (p.q_begin + job.q) * p.Kpad;
                     for (int c = 0; c < n_chunks; ++c) {
                         for (int ks = 0; ks < n_ks; ++ks, ++it) {
                             const uint32_t s = it % nstage, ph = (it / nstage) & 1;
-                            mbar_wait(&misc->empty[s], ph ^ 1);
+                            const long long tw = clock64();
+                            mbar_wait(&misc->empty[s], ph ^ 1);  // every CTA of the cluster has consumed the slot
+                            t_empty += clock64() - tw;
                             mbar_arrive_expect_tx(&misc->full[s], B_STAGE_BYTES);
-                            tma_load_2d(smem_b + (size_t)s * B_STAGE_BYTES, &tmap_b, &misc->full[s], ks * KSLICE,
-                                        row0 + c * CH);
+                            uint8_t* dst = smem_b + (size_t)s * B_STAGE_BYTES + crank * part_bytes;
+                            if (CL > 1)  // my 1/CL of the slice goes to every CTA of the cluster
+                                tma_load_2d_mc(dst, &tmap_b, &misc->full[s], ks * KSLICE,
+                                               row0 + c * CH + (int)crank * part_rows, cmask);
+                            else
+                                tma_load_2d(dst, &tmap_b, &misc->full[s], ks * KSLICE, row0 + c * CH);
                         }
                     }
                 }
+                if (p.prof) atomicAdd(p.prof + 16, (unsigned long long)t_empty);
             }
         } else if (warp == 1) {
             // ======================================================= MMA issuer
             const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CH);
             uint32_t it = 0, g = 0, aphase = 0;
+            long long t_full = 0, t_aready = 0, t_acc = 0;
             for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
                 const int sl = job.slot % nslots;
+                long long tw = clock64();
                 mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);
+                t_aready += clock64() - tw;
                 aphase ^= 1u << sl;
                 tc_fence_after_sync();
                 const uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
                 for (int c = 0; c < n_chunks; ++c, ++g) {
                     const uint32_t buf = g & 1, use = g >> 1;
+                    tw = clock64();
                     mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
+                    t_acc += clock64() - tw;
                     tc_fence_after_sync();
                     if (lane == 0) {
                         // the scan group has released this buffer: its norm slice can be replaced as well
@@ -183,7 +208,9 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     const uint32_t tmem_d = tmem_base + buf * CH;
                     for (int ks = 0; ks < n_ks; ++ks, ++it) {
                         const uint32_t s = it % nstage, ph = (it / nstage) & 1;
+                        tw = clock64();
                         mbar_wait(&misc->full[s], ph);
+                        t_full += clock64() - tw;
                         tc_fence_after_sync();
                         if (lane == 0) {
                             const uint64_t adesc = umma_desc_sw128(smem_u32(a_tile + (size_t)ks * A_SLICE_BYTES));
@@ -194,12 +221,21 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                                 umma_f16_ss(tmem_d, adesc + (uint64_t)(k16 * 2), bdesc + (uint64_t)(k16 * 2), idesc,
                                             (ks | k16) != 0);
                             }
-                            umma_commit(&misc->empty[s]);  // frees the ring slot when these MMAs retire
+                            // frees the ring slot (in every CTA of the cluster) when these MMAs retire
+                            if (CL > 1)
+                                umma_commit_mc(&misc->empty[s], cmask);
+                            else
+                                umma_commit(&misc->empty[s]);
                             if (ks == n_ks - 1) umma_commit(&misc->tmem_full[buf]);
                         }
                         __syncwarp();
                     }
                 }
+            }
+            if (p.prof && lane == 0) {
+                atomicAdd(p.prof + 17, (unsigned long long)t_full);
+                atomicAdd(p.prof + 18, (unsigned long long)t_aready);
+                atomicAdd(p.prof + 19, (unsigned long long)t_acc);
             }
         }
     } else if (warp < UPD_WARP0) {
@@ -298,6 +334,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             const uint32_t row_bytes = (uint32_t)d * 4u;
             uint32_t stg_par = 0, sphase = 0;
             long long t_upd = 0, t_wait = 0, t_rank = 0, t_gather = 0, t_apply = 0, t_tail = 0, t_acq = 0;
+            long long t_k1 = 0, t_k2 = 0, t_k3 = 0;
             unsigned long long n_dirty_tot = 0, n_multi_tot = 0, n_jobs = 0;
 
             // the staging buffer is handed from critical section to critical section in one global order:
@@ -401,114 +438,139 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 const uint32_t r0 = misc->g_rows[s][0][row], r1 = misc->g_rows[s][1][row];
                 const uint32_t c0m = misc->g_cols[s][0][row], c1m = misc->g_cols[s][1][row];
                 const int n0 = (int)((r0 >> 27) & 3u) * __popc(c0m), n1 = (int)((r1 >> 27) & 3u) * __popc(c1m);
-                int w = 0;
-                bool special = false;
+                int w = 0, mypos = -1;
                 if (((r0 | r1) & G_OVER) || n0 + n1 == 0) {
-                    const int pos = atomicAdd(&misc->n_dirty[s], 1);
-                    misc->dirty_rows[s][pos] = (uint8_t)row;
-                    misc->dirty_cols[s][pos] = (uint16_t)((c0m | c1m) ? (c0m | c1m) : 0xFFFFu);
-                    special = true;
+                    mypos = atomicAdd(&misc->n_special[s], 1);
+                    misc->special_rows[s][mypos] = (uint8_t)(row | 0x80);
                 } else if (n0 + n1 == 1) {
                     w = n0 ? (int)((r0 & IT_MASK) * 16u) + __ffs(c0m) - 1 : (int)((r1 & IT_MASK) * 16u) + __ffs(c1m) - 1;
                     w = max(0, min(w, Kv - 1));  // cannot bind (padding codes score 2^100); keeps the gather in bounds
                 } else {
-                    misc->score_rows[s][atomicAdd(&misc->n_score[s], 1)] = (uint8_t)row;
-                    special = true;
-                }
-                acquire(ticket);
-                const long long tj2 = clock64();
-                if (!special) {
-                    mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
-                    bulk_load_1d(stg_row, cbq + (size_t)w * d, row_bytes, &misc->stg_full[s]);
-                }
-                // frames that need exact scores expose their residual row in the staging buffer
-                if (__any_sync(0xffffffffu, special)) {
-#pragma unroll 1
-                    for (int c0 = 0; c0 < d; c0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_r + c0, v);
-                        tmem_ld_wait();
-                        if (special) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<uint4*>(stg_row + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        }
-                    }
+                    mypos = atomicAdd(&misc->n_special[s], 1);
+                    misc->special_rows[s][mypos] = (uint8_t)row;
                 }
                 named_bar_sync(bar_grp, GRP_THREADS);
-                // ---------------- exact re-rank (8 lanes per frame, 16 frames per pass)
-                const int n_score = misc->n_score[s], n_dirty = misc->n_dirty[s];
-                {
-                    const int sub = lane & 7, slot16 = (gw * 32 + lane) >> 3;
+                const long long tk1 = clock64();
+                t_k1 += tk1 - tj1;
+                // ---------------- exact scores for the frames that need them, RS_ROWS frames per round: their
+                // residual rows are exposed in shared memory, 8 lanes re-score one frame's candidates
+                const int n_special = misc->n_special[s];
+                float* rstage = rstage_all + (size_t)s * RS_ROWS * p.pitch;
 #pragma unroll 1
-                    for (int base = 0; base < n_score; base += GRP_THREADS / 8) {
-                        const int i = base + slot16;
-                        const bool sc = i < n_score;
-                        const int rr = misc->score_rows[s][sc ? i : 0];
-                        const CandSet cs(misc->g_rows[s][0][rr], misc->g_cols[s][0][rr], misc->g_rows[s][1][rr],
-                                         misc->g_cols[s][1][rr]);
-                        const int nc = sc ? cs.total() : 0;
-                        int nc_max = nc;  // the whole warp walks the longest list of its four frames
-                        nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, 8));
-                        nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, 16));
-                        const float* rrow = staging + (size_t)rr * p.pitch;
-                        float bs = __int_as_float(0x7f800000);
-                        int kwin = 0x7fffffff;
+                for (int base = 0; base < n_special; base += RS_ROWS) {
+                    const bool in_round = mypos >= base && mypos < base + RS_ROWS;
+                    int pair0 = 0, my_nc = 0;
+                    if (in_round && !(misc->special_rows[s][mypos] & 0x80)) {
+                        // list my (frame, candidate) pairs; too many for the round -> exact scan instead
+                        const CandSet cs(r0, c0m, r1, c1m);
+                        my_nc = cs.total();
+                        pair0 = atomicAdd(&misc->n_pairs[s], my_nc);
+                        if (pair0 + my_nc > MAX_PAIRS) {
+                            misc->special_rows[s][mypos] = (uint8_t)(row | 0x80);
+                            my_nc = 0;
+                        }
+                        for (int j = 0; j < my_nc; ++j)
+                            misc->pairs[s][pair0 + j] = ((uint32_t)(mypos - base) << 16) | (uint32_t)cs.code(j, Kv - 1);
+                    }
+                    if (__any_sync(0xffffffffu, in_round)) {
+                        float* dst = rstage + (size_t)(in_round ? mypos - base : 0) * p.pitch;
 #pragma unroll 1
-                        for (int j = 0; j < nc_max; j += 2) {
-                            const int k1 = cs.code(j, Kv - 1), k2 = cs.code(j + 1, Kv - 1);
-                            const float* cc[2] = {cbq + (size_t)k1 * d, cbq + (size_t)k2 * d};
-                            float sv[2];
-                            exact_score8_n<2>(rrow, cc, d, sub, sv);
-                            if (better(sv[0], k1, bs, kwin)) {
-                                bs = sv[0];
-                                kwin = k1;
-                            }
-                            if (better(sv[1], k2, bs, kwin)) {
-                                bs = sv[1];
-                                kwin = k2;
+                        for (int c0 = 0; c0 < d; c0 += 32) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(t_r + c0, v);
+                            tmem_ld_wait();
+                            if (in_round) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                             }
                         }
-                        if (sc && sub == 0) misc->win[s][rr] = kwin;
                     }
-                }
-                // ---------------- frames the filter could not bound: exact scan of the columns in reach
+                    named_bar_sync(bar_grp, GRP_THREADS);
+                    const long long tk2 = clock64();
+                    const int n_round = min(RS_ROWS, n_special - base);
+                    {
+                        // 16 groups of 8 lanes, four pairs per group per pass, every code load of a pass in flight
+                        const int sub = lane & 7, slot16 = (gw * 32 + lane) >> 3;
+                        const int np = min(misc->n_pairs[s], MAX_PAIRS);
 #pragma unroll 1
-                for (int i = 0; i < n_dirty; ++i) {
-                    const int rr = misc->dirty_rows[s][i];
-                    const uint32_t cols = misc->dirty_cols[s][i];
-                    const int n_it = (Kv + 15) / 16, per_w = (n_it + 3) / 4;
-                    const int it0 = min(n_it, gw * per_w), it1 = min(n_it, it0 + per_w);
-                    const ScoreIdx bsc = exact_scan_cols(staging + (size_t)rr * p.pitch, cbq, d, it0, it1, cols, Kv, lane);
-                    if (lane == 0) {
-                        misc->red_s[s][gw] = bsc.s;
-                        misc->red_k[s][gw] = bsc.k;
-                    }
-                    named_bar_sync(bar_grp, GRP_THREADS);
-                    if (gw == 0 && lane == 0) {
-                        float bs = misc->red_s[s][0];
-                        int bk = misc->red_k[s][0];
-                        for (int ww = 1; ww < 4; ++ww)
-                            if (better(misc->red_s[s][ww], misc->red_k[s][ww], bs, bk)) {
-                                bs = misc->red_s[s][ww];
-                                bk = misc->red_k[s][ww];
+                        for (int pb = 0; pb < np; pb += 64) {
+                            const float* rp[4];
+                            const float* cp[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const int pi = pb + t * 16 + slot16;
+                                const uint32_t e = misc->pairs[s][pi < np ? pi : 0];
+                                rp[t] = rstage + (size_t)(e >> 16) * p.pitch;
+                                cp[t] = cbq + (size_t)(e & 0xFFFFu) * d;
                             }
-                        if (bk < 0 || bk >= Kv) bk = 0;
-                        misc->win[s][rr] = bk;
+                            float sv[4];
+                            exact_score8_pairs<4>(rp, cp, d, sub, sv);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const int pi = pb + t * 16 + slot16;
+                                if (sub == 0 && pi < np) misc->pair_score[s][pi] = sv[t];
+                            }
+                        }
                     }
                     named_bar_sync(bar_grp, GRP_THREADS);
+                    if (my_nc > 0) {
+                        float bs = __int_as_float(0x7f800000);
+                        int kwin = 0x7fffffff;
+                        for (int j = 0; j < my_nc; ++j) {
+                            const float sc = misc->pair_score[s][pair0 + j];
+                            const int k = (int)(misc->pairs[s][pair0 + j] & 0xFFFFu);
+                            if (better(sc, k, bs, kwin)) {
+                                bs = sc;
+                                kwin = k;
+                            }
+                        }
+                        misc->win[s][row] = kwin;
+                    }
+                    const long long tk3 = clock64();
+                    if (base == 0) {
+                        t_k2 += tk2 - tk1;
+                        t_k3 += tk3 - tk2;
+                    }
+                    // frames the filter could not bound: exact scan of the columns in reach, all four warps
+#pragma unroll 1
+                    for (int i = 0; i < n_round; ++i) {
+                        const int ent = misc->special_rows[s][base + i];
+                        if (!(ent & 0x80)) continue;
+                        const int rr = ent & 0x7f;
+                        uint32_t cols = (uint32_t)misc->g_cols[s][0][rr] | (uint32_t)misc->g_cols[s][1][rr];
+                        if (cols == 0) cols = 0xFFFFu;
+                        const int n_it = (Kv + 15) / 16, per_w = (n_it + 3) / 4;
+                        const int it0 = min(n_it, gw * per_w), it1 = min(n_it, it0 + per_w);
+                        const ScoreIdx bsc = exact_scan_cols(rstage + (size_t)i * p.pitch, cbq, d, it0, it1, cols, Kv, lane);
+                        if (lane == 0) {
+                            misc->red_s[s][gw] = bsc.s;
+                            misc->red_k[s][gw] = bsc.k;
+                        }
+                        named_bar_sync(bar_grp, GRP_THREADS);
+                        if (gw == 0 && lane == 0) {
+                            float bs = misc->red_s[s][0];
+                            int bk = misc->red_k[s][0];
+                            for (int ww = 1; ww < 4; ++ww)
+                                if (better(misc->red_s[s][ww], misc->red_k[s][ww], bs, bk)) {
+                                    bs = misc->red_s[s][ww];
+                                    bk = misc->red_k[s][ww];
+                                }
+                            if (bk < 0 || bk >= Kv) bk = 0;
+                            misc->win[s][rr] = bk;
+                        }
+                        named_bar_sync(bar_grp, GRP_THREADS);
+                        ++n_dirty_tot;
+                    }
+                    if (gw == 0 && lane == 0) misc->n_pairs[s] = 0;  // every reader passed the barrier above
+                    named_bar_sync(bar_grp, GRP_THREADS);  // winners visible; the exposed rows may be replaced
                 }
-                named_bar_sync(bar_grp, GRP_THREADS);  // winners visible; residual rows in staging no longer read
-                if (gw == 0 && lane == 0) {
-                    misc->n_score[s] = 0;
-                    misc->n_dirty[s] = 0;
-                }
-                if (special) {
-                    w = misc->win[s][row];
-                    fence_proxy_async_smem();  // my generic-proxy writes of this staging row precede the bulk copy
-                    mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
-                    bulk_load_1d(stg_row, cbq + (size_t)w * d, row_bytes, &misc->stg_full[s]);
-                }
+                if (mypos >= 0) w = misc->win[s][row];
+                if (gw == 0 && lane == 0) misc->n_special[s] = 0;  // next use is after the next scan of this slot
+                const long long tj2 = clock64();
+                acquire(ticket);
+                mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
+                bulk_load_1d(stg_row, cbq + (size_t)w * d, row_bytes, &misc->stg_full[s]);
                 const long long tj3 = clock64();
                 // ---------------- constants of the next stage's operand (scale chosen from a bound known now)
                 const bool write_a = next_q_abs >= 0;
@@ -532,11 +594,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 const long long tj4 = clock64();
                 // ---------------- r <- r - c (fp32, tensor memory), next operand row, statistics row
                 float sq = 0.f;
-#pragma unroll 1
-                for (int c0 = 0; c0 < d; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(t_r + c0, v);
-                    tmem_ld_wait();
+                auto apply32 = [&](uint32_t (&v)[32], int c0) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 cv = *reinterpret_cast<const float4*>(stg_row + c0 + j);
@@ -557,6 +615,20 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     }
                     tmem_st_32x32(t_r + c0, v);
                     if (write_a) store_a32(a_tile, row, c0, v, sa);
+                };
+                {
+                    // two 32-feature pieces in flight: the next TMEM load is issued before the current piece is used
+                    uint32_t va[32], vb[32];
+                    tmem_ld_32x32(t_r, va);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < d; c0 += 64) {
+                        tmem_ld_wait();
+                        tmem_ld_32x32(t_r + c0 + 32, vb);  // d is a multiple of 64
+                        apply32(va, c0);
+                        tmem_ld_wait();
+                        if (c0 + 64 < d) tmem_ld_32x32(t_r + c0 + 64, va);
+                        apply32(vb, c0 + 32);
+                    }
                 }
                 if (stats) {
                     fence_proxy_async_smem();
@@ -642,14 +714,13 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 }
                 const long long tj6 = clock64();
                 t_wait += tj1 - tj0;
-                t_acq += tj2 - tj1;
-                t_rank += tj3 - tj2;
+                t_rank += tj2 - tj1;
+                t_acq += tj3 - tj2;
                 t_gather += tj4 - tj3;
                 t_apply += tj5 - tj4;
                 t_tail += tj6 - tj5;
                 t_upd += tj6 - tj1;
-                n_dirty_tot += n_dirty;
-                n_multi_tot += n_score;
+                n_multi_tot += n_special;
                 ++n_jobs;
             }
             bulk_wait0();  // my bulk stores / reductions are complete before the kernel ends
@@ -664,12 +735,16 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 atomicAdd(p.prof + 9, (unsigned long long)t_apply);
                 atomicAdd(p.prof + 10, (unsigned long long)t_gather);
                 atomicAdd(p.prof + 12, (unsigned long long)t_tail);
+                atomicAdd(p.prof + 13, (unsigned long long)t_k1);
+                atomicAdd(p.prof + 14, (unsigned long long)t_k2);
+                atomicAdd(p.prof + 15, (unsigned long long)t_k3);
             }
         }
     }
 
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
     if (threadIdx.x < nq) {
         const double v = misc->commit_acc[threadIdx.x];
         if (v != 0.0) atomicAdd(p.commit_sq + threadIdx.x, v);
@@ -731,7 +806,9 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     const uint32_t stg_bytes = (uint32_t)((TILE_M * p.pitch * 4 + 1023) / 1024 * 1024);
     const uint32_t misc_bytes = (uint32_t)((sizeof(tr::Misc) + 1023) / 1024 * 1024);
     p.off_stg = (uint32_t)p.nslots * a_bytes;
-    p.off_B = p.off_stg + stg_bytes;
+    p.off_rs = p.off_stg + stg_bytes;
+    const uint32_t rs_bytes = (uint32_t)((2 * tr::RS_ROWS * p.pitch * 4 + 1023) / 1024 * 1024);
+    p.off_B = p.off_rs + rs_bytes;
     const uint32_t fixed = p.off_B + misc_bytes + 1024;
     int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / tr::B_STAGE_BYTES) : 0;
     if (ns > tr::MAX_RING) ns = tr::MAX_RING;
@@ -751,7 +828,10 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nq_total * Kpad};
     const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)tr::CH};
+    static const int cluster_env = getenv("RVQ_CLUSTER") ? atoi(getenv("RVQ_CLUSTER")) : 2;
+    const int CL = (cluster_env == 1 || cluster_env == 2 || cluster_env == 4) ? cluster_env : 2;
+    p.cluster = CL;
+    const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)(tr::CH / CL)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(cb_op), gdim, gstride, box,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -761,7 +841,6 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
         return RVQ_ERR_CUDA;
     }
     const int num_tiles = (int)((N + TILE_M - 1) / TILE_M);
-    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
     p.x = x;
     p.N = N;
     p.ad = RowAddrT{L, sb, sl, sd};
@@ -780,13 +859,36 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     p.stats_cnt = stats_cnt;
     p.num_tiles = num_tiles;
     static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
-    if (want_prof && ws && ws_bytes >= 128) {
-        // counters live in the LAST 128 bytes of the workspace
-        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 128) & ~(size_t)7));
-        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 128, st));
+    if (want_prof && ws && ws_bytes >= 256) {
+        // 32 counters live in the LAST 256 bytes of the workspace
+        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 256) & ~(size_t)7));
+        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 256, st));
     }
     RVQ_CUDA(cudaFuncSetAttribute(tr::rvq_encode_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
-    tr::rvq_encode_tr_kernel<<<grid, tr::NUM_THREADS, smem_total, st>>>(tmap, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(tr::NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem_total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent grid: as many co-resident clusters as the device takes, not more than the tiles need
+    int max_clusters = num_sms / CL;
+    cfg.gridDim = dim3((unsigned)(max_clusters * CL), 1, 1);
+    {
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, tr::rvq_encode_tr_kernel, &cfg) == cudaSuccess && nc > 0 && nc < max_clusters)
+            max_clusters = nc;
+        (void)cudaGetLastError();
+    }
+    const int want_clusters = (num_tiles + CL - 1) / CL;
+    const int grid = (want_clusters < max_clusters ? want_clusters : max_clusters) * CL;
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    RVQ_CUDA(cudaLaunchKernelEx(&cfg, tr::rvq_encode_tr_kernel, tmap, p));
     RVQ_CUDA(cudaGetLastError());
     return RVQ_OK;
 }

@@ -32,7 +32,7 @@ with torch.no_grad():
 ev1.record()
 torch.cuda.synchronize()
 ws = q._ws
-prof = ws[(ws.numel() - 128) & ~7:][:128].view(torch.int64).cpu().tolist()
+prof = ws[(ws.numel() - 256) & ~7:][:256].view(torch.int64).cpu().tolist()
 n = max(prof[5], 1)
 ms = ev0.elapsed_time(ev1)
 ctas = min(148, (N + 127) // 128)
@@ -43,6 +43,9 @@ if d <= 128 and os.environ.get("RVQ_KERNEL") != "tc":
     print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+a_ready wait {prof[1]/n:.0f}, of scan: tmem_full wait {prof[11]/n:.0f})")
     print(f"  update group (per job): total={prof[2]/n:.0f} (+scan_done wait {prof[7]/n:.0f})  staging-acquire={prof[3]/n:.0f} "
           f"rerank={prof[8]/n:.0f} gather-wait={prof[10]/n:.0f} apply={prof[9]/n:.0f} tail={prof[12]/n:.0f}")
+    print(f"  rerank split: classify+barrier={prof[13]/n:.0f} expose-rows+barrier={prof[14]/n:.0f} score={prof[15]/n:.0f}")
+    print(f"  control warps per tile-stage: producer waits for a free ring slot={prof[16]/n:.0f}  MMA waits for codebook data={prof[17]/n:.0f} "
+          f"for the operand (a_ready)={prof[18]/n:.0f} for a free accumulator={prof[19]/n:.0f}")
     print(f"dirty rows per tile-stage={prof[4]/n:.3f}  multi-candidate rows per tile-stage={prof[6]/n:.2f}")
     sys.exit(0)
 print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+wait {prof[1]/n:.0f})  update={prof[2]/n:.0f} "
