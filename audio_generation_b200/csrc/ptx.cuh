@@ -206,6 +206,16 @@ __device__ __forceinline__ void reg_dealloc() {
 }
 
 
+
+// 16-byte asynchronous copy global -> shared (LDGSTS, generic proxy); completion is collected per thread by
+// cp_async_arrive_noinc on an mbarrier whose expected count already includes that arrival
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ----------------------------------------------------------------------------- thread-block clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

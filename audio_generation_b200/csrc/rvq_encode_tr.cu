@@ -41,8 +41,7 @@ constexpr uint32_t B_STAGE_BYTES = CH * KSLICE * 2;  // 16 KiB
 constexpr uint32_t BAR_SCAN = 1;                     // named barrier of the 256 scan threads
 constexpr uint32_t BAR_GRP0 = 2;                     // + slot: named barrier of one update group
 constexpr uint32_t TMEM_RES_COL = 256;               // first residual column
-constexpr int MAX_PAIRS = 128;  // (frame, candidate) pairs one re-rank round can score
-constexpr int RS_ROWS = 16;  // residual rows one update group can expose per re-rank round (8 lanes per frame)
+constexpr int RS_ROWS = 16;  // re-rank entries (residual row + four candidates) per round: 8 lanes per entry
 
 struct Params {
     const float* x;
@@ -73,32 +72,14 @@ struct __align__(16) Misc {
     uint32_t g_rows[2][2][TILE_M];  // [slot][group][frame]: loads that may hold a candidate
     uint16_t g_cols[2][2][TILE_M];  // [slot][group][frame]: columns that may hold a candidate
     int win[2][TILE_M];             // [slot][frame]: selected code
-    int n_special[2], n_pairs[2];
-    uint32_t pairs[2][MAX_PAIRS];     // [slot][i]: (exposed row slot << 16) | code
-    float pair_score[2][MAX_PAIRS];
-    uint8_t special_rows[2][TILE_M];  // [slot][i]: frame | 0x80 if it needs the exact scan
+    int n_special[2], n_dirty[2];
+    uint32_t pairs[2][RS_ROWS * 4];      // [slot][entry * 4 + t]: code scored
+    float pair_score[2][RS_ROWS * 4];    // its exact score
+    uint16_t special_rows[2][4 * TILE_M];  // [slot][entry]: frame | block << 8 | 0x8000 if it needs the exact scan
     float red_s[2][4];
     int red_k[2][4];
     double commit_acc[MAX_NQ];
 };
-
-// 32 consecutive features of one frame -> fp16 operand (scaled by sa) in the UMMA A tile
-__device__ __forceinline__ void store_a32(uint8_t* a_tile, int row, int c0, const uint32_t (&v)[32], float sa) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-        uint4 pk;
-        __half2 h;
-        h = __floats2half2_rn(__uint_as_float(v[j + 0]) * sa, __uint_as_float(v[j + 1]) * sa);
-        pk.x = *reinterpret_cast<const uint32_t*>(&h);
-        h = __floats2half2_rn(__uint_as_float(v[j + 2]) * sa, __uint_as_float(v[j + 3]) * sa);
-        pk.y = *reinterpret_cast<const uint32_t*>(&h);
-        h = __floats2half2_rn(__uint_as_float(v[j + 4]) * sa, __uint_as_float(v[j + 5]) * sa);
-        pk.z = *reinterpret_cast<const uint32_t*>(&h);
-        h = __floats2half2_rn(__uint_as_float(v[j + 6]) * sa, __uint_as_float(v[j + 7]) * sa);
-        pk.w = *reinterpret_cast<const uint32_t*>(&h);
-        *reinterpret_cast<uint4*>(a_tile + a_tile_offset(row, c0 + j)) = pk;
-    }
-}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
@@ -134,7 +115,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             mbar_init(&misc->scan_done[i], SCAN_THREADS);
             mbar_init(&misc->stg_full[i], GRP_THREADS);
             misc->n_special[i] = 0;
-            misc->n_pairs[i] = 0;
+            misc->n_dirty[i] = 0;
         }
         mbar_init(&misc->stg_free, GRP_THREADS);
         for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
@@ -155,88 +136,84 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
         reg_dealloc<40>();
         if (warp == 0) {
             // ======================================================= TMA producer (codebook slices)
-            if (lane == 0) {
-                uint32_t it = 0;
-                long long t_empty = 0;
+            if (elect_one()) {
+                uint32_t st = 0, ph = 0;
                 const uint32_t part_bytes = B_STAGE_BYTES / (uint32_t)CL;
                 const int part_rows = CH / CL;
                 for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
-                    const int row0 = (p.q_begin + job.q) * p.Kpad;
+                    const int row0 = (p.q_begin + job.q) * p.Kpad + (int)crank * part_rows;
                     for (int c = 0; c < n_chunks; ++c) {
-                        for (int ks = 0; ks < n_ks; ++ks, ++it) {
-                            const uint32_t s = it % nstage, ph = (it / nstage) & 1;
-                            const long long tw = clock64();
-                            mbar_wait(&misc->empty[s], ph ^ 1);  // every CTA of the cluster has consumed the slot
-                            t_empty += clock64() - tw;
-                            mbar_arrive_expect_tx(&misc->full[s], B_STAGE_BYTES);
-                            uint8_t* dst = smem_b + (size_t)s * B_STAGE_BYTES + crank * part_bytes;
+                        for (int ks = 0; ks < n_ks; ++ks) {
+                            mbar_wait(&misc->empty[st], ph ^ 1);  // every CTA of the cluster has consumed the slot
+                            mbar_arrive_expect_tx(&misc->full[st], B_STAGE_BYTES);
+                            uint8_t* dst = smem_b + (size_t)st * B_STAGE_BYTES + crank * part_bytes;
                             if (CL > 1)  // my 1/CL of the slice goes to every CTA of the cluster
-                                tma_load_2d_mc(dst, &tmap_b, &misc->full[s], ks * KSLICE,
-                                               row0 + c * CH + (int)crank * part_rows, cmask);
+                                tma_load_2d_mc(dst, &tmap_b, &misc->full[st], ks * KSLICE, row0 + c * CH, cmask);
                             else
-                                tma_load_2d(dst, &tmap_b, &misc->full[s], ks * KSLICE, row0 + c * CH);
+                                tma_load_2d(dst, &tmap_b, &misc->full[st], ks * KSLICE, row0 + c * CH);
+                            if (++st == (uint32_t)nstage) {
+                                st = 0;
+                                ph ^= 1u;
+                            }
                         }
                     }
                 }
-                if (p.prof) atomicAdd(p.prof + 16, (unsigned long long)t_empty);
             }
+            __syncwarp();
         } else if (warp == 1) {
             // ======================================================= MMA issuer
-            const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CH);
-            uint32_t it = 0, g = 0, aphase = 0;
-            long long t_full = 0, t_aready = 0, t_acc = 0;
-            for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
-                const int sl = job.slot % nslots;
-                long long tw = clock64();
-                mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);
-                t_aready += clock64() - tw;
-                aphase ^= 1u << sl;
-                tc_fence_after_sync();
-                const uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
-                for (int c = 0; c < n_chunks; ++c, ++g) {
-                    const uint32_t buf = g & 1, use = g >> 1;
-                    tw = clock64();
-                    mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
-                    t_acc += clock64() - tw;
+            // ONE elected thread runs the whole loop: every instruction of a lone warp costs ~8 cycles of latency,
+            // and a 128 x 128 x 16 MMA lasts 64 cycles, so the issue loop must stay at a handful of instructions
+            // per MMA (no divisions, no per-iteration warp syncs, descriptors advanced by additions).
+            if (elect_one()) {
+                const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CH);
+                const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_b));
+                uint32_t g = 0, aphase = 0, st = 0, ph = 0;
+                long long t_aready = 0;
+                for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+                    const int sl = job.slot % nslots;
+                    const long long tw = clock64();
+                    mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);
+                    t_aready += clock64() - tw;
+                    aphase ^= 1u << sl;
                     tc_fence_after_sync();
-                    if (lane == 0) {
+                    const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + (size_t)sl * a_tile_bytes));
+                    const float* nsrc = p.cb_norm + (size_t)(p.q_begin + job.q) * p.Kpad;
+                    for (int c = 0; c < n_chunks; ++c, ++g) {
+                        const uint32_t buf = g & 1, use = g >> 1;
+                        mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
+                        tc_fence_after_sync();
                         // the scan group has released this buffer: its norm slice can be replaced as well
                         mbar_arrive_expect_tx(&misc->norm_full[buf], CH * 4);
-                        bulk_load_1d(misc->norms[buf], p.cb_norm + (size_t)(p.q_begin + job.q) * p.Kpad + c * CH, CH * 4,
-                                     &misc->norm_full[buf]);
-                    }
-                    const uint32_t tmem_d = tmem_base + buf * CH;
-                    for (int ks = 0; ks < n_ks; ++ks, ++it) {
-                        const uint32_t s = it % nstage, ph = (it / nstage) & 1;
-                        tw = clock64();
-                        mbar_wait(&misc->full[s], ph);
-                        t_full += clock64() - tw;
-                        tc_fence_after_sync();
-                        if (lane == 0) {
-                            const uint64_t adesc = umma_desc_sw128(smem_u32(a_tile + (size_t)ks * A_SLICE_BYTES));
-                            const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)s * B_STAGE_BYTES));
-#pragma unroll
-                            for (int k16 = 0; k16 < KSLICE / 16; ++k16) {
-                                // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
-                                umma_f16_ss(tmem_d, adesc + (uint64_t)(k16 * 2), bdesc + (uint64_t)(k16 * 2), idesc,
-                                            (ks | k16) != 0);
-                            }
+                        bulk_load_1d(misc->norms[buf], nsrc + c * CH, CH * 4, &misc->norm_full[buf]);
+                        const uint32_t tmem_d = tmem_base + buf * CH;
+                        uint64_t adesc = adesc0;
+                        for (int ks = 0; ks < n_ks; ++ks) {
+                            mbar_wait(&misc->full[st], ph);
+                            tc_fence_after_sync();
+                            const uint64_t bdesc = bdesc0 + (uint64_t)(st * (B_STAGE_BYTES >> 4));
+                            // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
+                            umma_f16_ss(tmem_d, adesc, bdesc, idesc, ks != 0);
+                            umma_f16_ss(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
+                            umma_f16_ss(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
+                            umma_f16_ss(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
                             // frees the ring slot (in every CTA of the cluster) when these MMAs retire
                             if (CL > 1)
-                                umma_commit_mc(&misc->empty[s], cmask);
+                                umma_commit_mc(&misc->empty[st], cmask);
                             else
-                                umma_commit(&misc->empty[s]);
-                            if (ks == n_ks - 1) umma_commit(&misc->tmem_full[buf]);
+                                umma_commit(&misc->empty[st]);
+                            adesc += (uint64_t)(A_SLICE_BYTES >> 4);
+                            if (++st == (uint32_t)nstage) {
+                                st = 0;
+                                ph ^= 1u;
+                            }
                         }
-                        __syncwarp();
+                        umma_commit(&misc->tmem_full[buf]);
                     }
                 }
+                if (p.prof) atomicAdd(p.prof + 18, (unsigned long long)t_aready);
             }
-            if (p.prof && lane == 0) {
-                atomicAdd(p.prof + 17, (unsigned long long)t_full);
-                atomicAdd(p.prof + 18, (unsigned long long)t_aready);
-                atomicAdd(p.prof + 19, (unsigned long long)t_acc);
-            }
+            __syncwarp();
         }
     } else if (warp < UPD_WARP0) {
         reg_dealloc<88>();
@@ -328,7 +305,11 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
         if (s < nslots) {
             const uint32_t t_r = tmem_base + ((uint32_t)(gw * 32) << 16) + TMEM_RES_COL + (uint32_t)(s * d);
             float* stg_row = staging + (size_t)row * p.pitch;
+            float* stg_warp = staging + (size_t)(gw * 32) * p.pitch;  // first staging row of this warp's frames
             uint8_t* a_tile = smem + (size_t)s * a_tile_bytes;
+            // A-tile address pieces of my frame: 16-byte chunk j of a 128-byte swizzle row sits at (j ^ (row & 7)) << 4
+            uint8_t* a_row = a_tile + (uint32_t)row * 128u;
+            const uint32_t rx = ((uint32_t)row & 7u) << 4;
             const bool row_major = (p.ad.sd == 1);
             const uint32_t bar_grp = BAR_GRP0 + (uint32_t)s;
             const uint32_t row_bytes = (uint32_t)d * 4u;
@@ -347,6 +328,56 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 mbar_wait(&misc->stg_full[s], stg_par);
                 stg_par ^= 1u;
             };
+            // 32 consecutive features (c0 .. c0+31, inside one 64-feature slice) of my frame -> fp16 operand
+            auto store_a = [&](int c0, const uint32_t (&v)[32], float sa) {
+                uint8_t* base = a_row + (uint32_t)(c0 >> 6) * A_SLICE_BYTES;
+                const uint32_t j0 = ((uint32_t)c0 >> 3) & 7u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    __half2 h;
+                    h = __floats2half2_rn(__uint_as_float(v[8 * j + 0]) * sa, __uint_as_float(v[8 * j + 1]) * sa);
+                    pk.x = *reinterpret_cast<const uint32_t*>(&h);
+                    h = __floats2half2_rn(__uint_as_float(v[8 * j + 2]) * sa, __uint_as_float(v[8 * j + 3]) * sa);
+                    pk.y = *reinterpret_cast<const uint32_t*>(&h);
+                    h = __floats2half2_rn(__uint_as_float(v[8 * j + 4]) * sa, __uint_as_float(v[8 * j + 5]) * sa);
+                    pk.z = *reinterpret_cast<const uint32_t*>(&h);
+                    h = __floats2half2_rn(__uint_as_float(v[8 * j + 6]) * sa, __uint_as_float(v[8 * j + 7]) * sa);
+                    pk.w = *reinterpret_cast<const uint32_t*>(&h);
+                    *reinterpret_cast<uint4*>(base + ((((j0 + (uint32_t)j) << 4)) ^ rx)) = pk;
+                }
+            };
+            // Coalesced asynchronous gather of one d-float row per frame of this warp into the staging buffer:
+            // lane r's row number (index into `table`, rows of d floats; < 0 = none) is broadcast and the 32 lanes
+            // copy 16 bytes each (d <= 128: one instruction per row).  Every thread then arrives on stg_full[s]
+            // when ITS copies have landed (count = 128 arrivals).
+            // `off_mine`: element offset of my frame inside `table` (< 0 = no frame)
+            auto gather_rows = [&](const float* table, long long off_mine) {
+                __syncwarp();  // every lane has finished with the staging rows of this warp
+                const int lo = (int)(off_mine & 0xffffffffll), hi = (int)(off_mine >> 32);
+                const float* src_lane = table + lane * 4;
+                float* dst_lane = stg_warp + lane * 4;
+                const bool lane_on = lane * 4 < d;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const int rlo = __shfl_sync(0xffffffffu, lo, r), rhi = __shfl_sync(0xffffffffu, hi, r);
+                    const long long ro = ((long long)rhi << 32) | (unsigned int)rlo;
+                    if (ro >= 0 && lane_on) cp_async16(dst_lane + (size_t)r * p.pitch, src_lane + ro);
+                }
+                cp_async_arrive_noinc(&misc->stg_full[s]);
+            };
+            auto gather_codes = [&](const float* cbq_, int w_mine) {
+                __syncwarp();
+                const float* src_lane = cbq_ + lane * 4;
+                float* dst_lane = stg_warp + lane * 4;
+                const bool lane_on = lane * 4 < d;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const int wr = __shfl_sync(0xffffffffu, w_mine, r);
+                    if (lane_on) cp_async16(dst_lane + (size_t)r * p.pitch, src_lane + (size_t)wr * d);
+                }
+                cp_async_arrive_noinc(&misc->stg_full[s]);
+            };
 
             // load tile `tile` into this slot (staging held): residual <- x, fp16 operand + row constants of stage 0
             auto load_tile = [&](int tile) {
@@ -354,12 +385,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 const bool valid = n < p.N;
                 const long long off = valid ? p.ad.row(n) : 0;
                 if (row_major) {
-                    if (valid) {
-                        mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
-                        bulk_load_1d(stg_row, p.x + off, row_bytes, &misc->stg_full[s]);
-                    } else {
-                        mbar_arrive(&misc->stg_full[s]);
-                    }
+                    gather_rows(p.x, valid ? off : -1);
                     wait_staging();
                 }
                 float sq = 0.f, amax = 0.f;
@@ -402,7 +428,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     uint32_t v[32];
                     tmem_ld_32x32(t_r + c0, v);
                     tmem_ld_wait();
-                    store_a32(a_tile, row, c0, v, sa);
+                    store_a(c0, v, sa);
                 }
                 float na, delta;
                 row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
@@ -434,46 +460,44 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 mbar_wait(&misc->scan_done[s], sphase);
                 sphase ^= 1u;
                 const long long tj1 = clock64();
-                // ---------------- classify my frame: certified (one candidate), several candidates, exact scan
+                // ---------------- classify my frame: certified (one candidate), several candidates, exact scan.
+                // A frame with nc candidates takes ceil(nc / 4) re-rank entries (four candidates per entry).
                 const uint32_t r0 = misc->g_rows[s][0][row], r1 = misc->g_rows[s][1][row];
                 const uint32_t c0m = misc->g_cols[s][0][row], c1m = misc->g_cols[s][1][row];
                 const int n0 = (int)((r0 >> 27) & 3u) * __popc(c0m), n1 = (int)((r1 >> 27) & 3u) * __popc(c1m);
-                int w = 0, mypos = -1;
-                if (((r0 | r1) & G_OVER) || n0 + n1 == 0) {
-                    mypos = atomicAdd(&misc->n_special[s], 1);
-                    misc->special_rows[s][mypos] = (uint8_t)(row | 0x80);
-                } else if (n0 + n1 == 1) {
+                const int nc = n0 + n1;
+                int w = 0, mypos = -1, myk = 0;
+                bool dirty = false;
+                if (((r0 | r1) & G_OVER) || nc == 0 || nc > 16) {
+                    dirty = true;
+                    myk = 1;
+                } else if (nc == 1) {
                     w = n0 ? (int)((r0 & IT_MASK) * 16u) + __ffs(c0m) - 1 : (int)((r1 & IT_MASK) * 16u) + __ffs(c1m) - 1;
                     w = max(0, min(w, Kv - 1));  // cannot bind (padding codes score 2^100); keeps the gather in bounds
                 } else {
-                    mypos = atomicAdd(&misc->n_special[s], 1);
-                    misc->special_rows[s][mypos] = (uint8_t)row;
+                    myk = (nc + 3) >> 2;
                 }
-                named_bar_sync(bar_grp, GRP_THREADS);
+                if (myk > 0) {
+                    mypos = atomicAdd(&misc->n_special[s], myk);
+                    for (int i = 0; i < myk; ++i)
+                        misc->special_rows[s][mypos + i] = (uint16_t)(row | (i << 8) | (dirty ? 0x8000 : 0));
+                    if (dirty) atomicAdd(&misc->n_dirty[s], 1);
+                }
+                // ---------------- exact scores, RS_ROWS entries per round: the frames expose their residual rows
+                // in shared memory and every 8-lane group re-scores the four candidates of one entry
+                float* rstage = rstage_all + (size_t)s * RS_ROWS * p.pitch;
+                float bs = __int_as_float(0x7f800000);
+                int kwin = 0x7fffffff;
+                int n_special = RS_ROWS, n_dirty = 0;  // read after the first barrier of round 0
                 const long long tk1 = clock64();
                 t_k1 += tk1 - tj1;
-                // ---------------- exact scores for the frames that need them, RS_ROWS frames per round: their
-                // residual rows are exposed in shared memory, 8 lanes re-score one frame's candidates
-                const int n_special = misc->n_special[s];
-                float* rstage = rstage_all + (size_t)s * RS_ROWS * p.pitch;
 #pragma unroll 1
                 for (int base = 0; base < n_special; base += RS_ROWS) {
-                    const bool in_round = mypos >= base && mypos < base + RS_ROWS;
-                    int pair0 = 0, my_nc = 0;
-                    if (in_round && !(misc->special_rows[s][mypos] & 0x80)) {
-                        // list my (frame, candidate) pairs; too many for the round -> exact scan instead
-                        const CandSet cs(r0, c0m, r1, c1m);
-                        my_nc = cs.total();
-                        pair0 = atomicAdd(&misc->n_pairs[s], my_nc);
-                        if (pair0 + my_nc > MAX_PAIRS) {
-                            misc->special_rows[s][mypos] = (uint8_t)(row | 0x80);
-                            my_nc = 0;
-                        }
-                        for (int j = 0; j < my_nc; ++j)
-                            misc->pairs[s][pair0 + j] = ((uint32_t)(mypos - base) << 16) | (uint32_t)cs.code(j, Kv - 1);
-                    }
+                    // my first entry inside this round (if any) is where my row is exposed
+                    const int lo = max(mypos, base), hi = min(mypos + myk, base + RS_ROWS);
+                    const bool in_round = mypos >= 0 && lo < hi;
                     if (__any_sync(0xffffffffu, in_round)) {
-                        float* dst = rstage + (size_t)(in_round ? mypos - base : 0) * p.pitch;
+                        float* dst = rstage + (size_t)(in_round ? lo - base : 0) * p.pitch;
 #pragma unroll 1
                         for (int c0 = 0; c0 < d; c0 += 32) {
                             uint32_t v[32];
@@ -486,46 +510,55 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                             }
                         }
                     }
-                    named_bar_sync(bar_grp, GRP_THREADS);
+                    named_bar_sync(bar_grp, GRP_THREADS);  // entries listed (round 0) and rows exposed
+                    if (base == 0) {
+                        n_special = misc->n_special[s];
+                        n_dirty = misc->n_dirty[s];
+                    }
                     const long long tk2 = clock64();
                     const int n_round = min(RS_ROWS, n_special - base);
                     {
-                        // 16 groups of 8 lanes, four pairs per group per pass, every code load of a pass in flight
                         const int sub = lane & 7, slot16 = (gw * 32 + lane) >> 3;
-                        const int np = min(misc->n_pairs[s], MAX_PAIRS);
-#pragma unroll 1
-                        for (int pb = 0; pb < np; pb += 64) {
-                            const float* rp[4];
-                            const float* cp[4];
+                        const int ent = slot16 < n_round ? misc->special_rows[s][base + slot16] : 0x8000;
+                        if (__any_sync(0xffffffffu, !(ent & 0x8000))) {
+                            const int rr = ent & 0x7f, blk = (ent >> 8) & 0x7f;
+                            const CandSet cs(misc->g_rows[s][0][rr], misc->g_cols[s][0][rr], misc->g_rows[s][1][rr],
+                                             misc->g_cols[s][1][rr]);
+                            // the frame's row sits at its first entry of this round
+                            const int first = max(slot16 - blk, 0);
+                            const float* rrow = rstage + (size_t)first * p.pitch;
+                            int k[4];
+                            const float* cc[4];
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
-                                const int pi = pb + t * 16 + slot16;
-                                const uint32_t e = misc->pairs[s][pi < np ? pi : 0];
-                                rp[t] = rstage + (size_t)(e >> 16) * p.pitch;
-                                cp[t] = cbq + (size_t)(e & 0xFFFFu) * d;
+                                k[t] = cs.code(4 * blk + t, Kv - 1);
+                                cc[t] = cbq + (size_t)k[t] * d;
                             }
                             float sv[4];
-                            exact_score8_pairs<4>(rp, cp, d, sub, sv);
+                            exact_score8_n<4>(rrow, cc, d, sub, sv);
+                            if (sub == 0 && !(ent & 0x8000)) {
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const int pi = pb + t * 16 + slot16;
-                                if (sub == 0 && pi < np) misc->pair_score[s][pi] = sv[t];
+                                for (int t = 0; t < 4; ++t) {
+                                    misc->pair_score[s][slot16 * 4 + t] = sv[t];
+                                    misc->pairs[s][slot16 * 4 + t] = (uint32_t)k[t];
+                                }
                             }
                         }
                     }
                     named_bar_sync(bar_grp, GRP_THREADS);
-                    if (my_nc > 0) {
-                        float bs = __int_as_float(0x7f800000);
-                        int kwin = 0x7fffffff;
-                        for (int j = 0; j < my_nc; ++j) {
-                            const float sc = misc->pair_score[s][pair0 + j];
-                            const int k = (int)(misc->pairs[s][pair0 + j] & 0xFFFFu);
-                            if (better(sc, k, bs, kwin)) {
-                                bs = sc;
-                                kwin = k;
+                    if (in_round && !dirty) {
+                        for (int e = lo; e < hi; ++e) {
+                            const int blk = e - mypos;
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float sc = misc->pair_score[s][(e - base) * 4 + t];
+                                const int kk = (int)misc->pairs[s][(e - base) * 4 + t];
+                                if (4 * blk + t < nc && better(sc, kk, bs, kwin)) {
+                                    bs = sc;
+                                    kwin = kk;
+                                }
                             }
                         }
-                        misc->win[s][row] = kwin;
                     }
                     const long long tk3 = clock64();
                     if (base == 0) {
@@ -533,44 +566,48 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                         t_k3 += tk3 - tk2;
                     }
                     // frames the filter could not bound: exact scan of the columns in reach, all four warps
+                    if (n_dirty > 0) {
 #pragma unroll 1
-                    for (int i = 0; i < n_round; ++i) {
-                        const int ent = misc->special_rows[s][base + i];
-                        if (!(ent & 0x80)) continue;
-                        const int rr = ent & 0x7f;
-                        uint32_t cols = (uint32_t)misc->g_cols[s][0][rr] | (uint32_t)misc->g_cols[s][1][rr];
-                        if (cols == 0) cols = 0xFFFFu;
-                        const int n_it = (Kv + 15) / 16, per_w = (n_it + 3) / 4;
-                        const int it0 = min(n_it, gw * per_w), it1 = min(n_it, it0 + per_w);
-                        const ScoreIdx bsc = exact_scan_cols(rstage + (size_t)i * p.pitch, cbq, d, it0, it1, cols, Kv, lane);
-                        if (lane == 0) {
-                            misc->red_s[s][gw] = bsc.s;
-                            misc->red_k[s][gw] = bsc.k;
+                        for (int i = 0; i < n_round; ++i) {
+                            const int ent = misc->special_rows[s][base + i];
+                            if (!(ent & 0x8000)) continue;
+                            const int rr = ent & 0x7f;
+                            uint32_t cols = (uint32_t)misc->g_cols[s][0][rr] | (uint32_t)misc->g_cols[s][1][rr];
+                            if (cols == 0) cols = 0xFFFFu;
+                            const int n_it = (Kv + 15) / 16, per_w = (n_it + 3) / 4;
+                            const int it0 = min(n_it, gw * per_w), it1 = min(n_it, it0 + per_w);
+                            const ScoreIdx bsc =
+                                exact_scan_cols(rstage + (size_t)i * p.pitch, cbq, d, it0, it1, cols, Kv, lane);
+                            if (lane == 0) {
+                                misc->red_s[s][gw] = bsc.s;
+                                misc->red_k[s][gw] = bsc.k;
+                            }
+                            named_bar_sync(bar_grp, GRP_THREADS);
+                            if (gw == 0 && lane == 0) {
+                                float rs_ = misc->red_s[s][0];
+                                int rk_ = misc->red_k[s][0];
+                                for (int ww = 1; ww < 4; ++ww)
+                                    if (better(misc->red_s[s][ww], misc->red_k[s][ww], rs_, rk_)) {
+                                        rs_ = misc->red_s[s][ww];
+                                        rk_ = misc->red_k[s][ww];
+                                    }
+                                if (rk_ < 0 || rk_ >= Kv) rk_ = 0;
+                                misc->win[s][rr] = rk_;
+                            }
+                            named_bar_sync(bar_grp, GRP_THREADS);
+                            ++n_dirty_tot;
                         }
-                        named_bar_sync(bar_grp, GRP_THREADS);
-                        if (gw == 0 && lane == 0) {
-                            float bs = misc->red_s[s][0];
-                            int bk = misc->red_k[s][0];
-                            for (int ww = 1; ww < 4; ++ww)
-                                if (better(misc->red_s[s][ww], misc->red_k[s][ww], bs, bk)) {
-                                    bs = misc->red_s[s][ww];
-                                    bk = misc->red_k[s][ww];
-                                }
-                            if (bk < 0 || bk >= Kv) bk = 0;
-                            misc->win[s][rr] = bk;
-                        }
-                        named_bar_sync(bar_grp, GRP_THREADS);
-                        ++n_dirty_tot;
                     }
-                    if (gw == 0 && lane == 0) misc->n_pairs[s] = 0;  // every reader passed the barrier above
-                    named_bar_sync(bar_grp, GRP_THREADS);  // winners visible; the exposed rows may be replaced
+                    if (base + RS_ROWS < n_special) named_bar_sync(bar_grp, GRP_THREADS);  // exposed rows are replaced
                 }
-                if (mypos >= 0) w = misc->win[s][row];
-                if (gw == 0 && lane == 0) misc->n_special[s] = 0;  // next use is after the next scan of this slot
+                if (mypos >= 0) w = dirty ? misc->win[s][row] : min(kwin, Kv - 1);
+                if (gw == 0 && lane == 0) {  // next use is after the next scan of this slot
+                    misc->n_special[s] = 0;
+                    misc->n_dirty[s] = 0;
+                }
                 const long long tj2 = clock64();
                 acquire(ticket);
-                mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
-                bulk_load_1d(stg_row, cbq + (size_t)w * d, row_bytes, &misc->stg_full[s]);
+                gather_codes(cbq, w);
                 const long long tj3 = clock64();
                 // ---------------- constants of the next stage's operand (scale chosen from a bound known now)
                 const bool write_a = next_q_abs >= 0;
@@ -614,7 +651,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                         v[j + 3] = __float_as_uint(n3f);
                     }
                     tmem_st_32x32(t_r + c0, v);
-                    if (write_a) store_a32(a_tile, row, c0, v, sa);
+                    if (write_a) store_a(c0, v, sa);
                 };
                 {
                     // two 32-feature pieces in flight: the next TMEM load is issued before the current piece is used
@@ -663,12 +700,8 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     // ---------------- last stage: xq = x - final residual, then the slot takes its next tile
                     const long long off = valid ? p.ad.row(n) : 0;
                     if (row_major) {
-                        if (valid) {
-                            mbar_arrive_expect_tx(&misc->stg_full[s], row_bytes);
-                            bulk_load_1d(stg_row, p.x + off, row_bytes, &misc->stg_full[s]);
-                        } else {
-                            mbar_arrive(&misc->stg_full[s]);
-                        }
+                        if (stats) fence_proxy_async_smem();
+                        gather_rows(p.x, valid ? off : -1);
                         wait_staging();
                     }
 #pragma unroll 1
@@ -695,12 +728,17 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                         }
                     }
                     if (row_major) {
-                        fence_proxy_async_smem();
-                        if (valid) {
-                            bulk_store_1d(p.xq + off, stg_row, row_bytes);
-                            bulk_commit();
-                            bulk_wait_read0();
+                        // coalesced store of the warp's 32 output rows (512 bytes per instruction)
+                        __syncwarp();
+                        const unsigned long long dp = valid ? reinterpret_cast<unsigned long long>(p.xq + off) : 0ull;
+#pragma unroll 4
+                        for (int r = 0; r < 32; ++r) {
+                            const unsigned long long dpr = __shfl_sync(0xffffffffu, dp, r);
+                            if (dpr != 0ull && lane * 4 < d)
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(dpr) + lane * 4) =
+                                    *reinterpret_cast<const float4*>(stg_warp + (size_t)r * p.pitch + lane * 4);
                         }
+                        __syncwarp();
                     }
                     const int next_i = job.i + nslots;
                     if (next_i < n_local) {
@@ -708,7 +746,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                         release();
                         mbar_arrive(&misc->a_ready[s]);
                     } else {
-                        fence_proxy_async_smem();
                         release();
                     }
                 }
@@ -723,7 +760,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 n_multi_tot += n_special;
                 ++n_jobs;
             }
-            bulk_wait0();  // my bulk stores / reductions are complete before the kernel ends
+            bulk_wait0();  // my bulk reductions are complete before the kernel ends
             if (p.prof && gw == 0 && lane == 0) {
                 atomicAdd(p.prof + 2, (unsigned long long)t_upd);
                 atomicAdd(p.prof + 3, (unsigned long long)t_acq);
