@@ -105,6 +105,32 @@ __device__ __forceinline__ void scan16_2d(const uint32_t (&v)[16], const float* 
     m4 = fminf(m4, w);
 }
 
+// same for accumulators that already contain the norm term (rvq_encode_tr.cu folds it into the MMA)
+__device__ __forceinline__ void scan16_2d_raw(const uint32_t (&v)[16], uint32_t it, float (&Cm)[16], float& m1, float& m2, float& m3, float& m4,
+                                          float* dbg) {
+    float s[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[j] = __uint_as_float(v[j]);
+    if (dbg) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dbg[j] = s[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) Cm[j] = fminf(Cm[j], s[j]);
+    float r = fminf(fminf(s[0], s[1]), s[2]);
+#pragma unroll
+    for (int j = 3; j < 15; j += 2) r = fminf(fminf(r, s[j]), s[j + 1]);
+    r = fminf(r, s[15]);
+    const float rp = __uint_as_float((__float_as_uint(r) & ~IT_MASK) | it);
+    const float t = fmaxf(m1, rp);
+    m1 = fminf(m1, rp);
+    const float u = fmaxf(m2, t);
+    m2 = fminf(m2, t);
+    const float w = fmaxf(m3, u);
+    m3 = fminf(m3, u);
+    m4 = fminf(m4, w);
+}
+
 // enumeration of {loads} x {columns} of both scan groups
 struct CandSet {
     uint32_t r[2], c[2];

@@ -115,6 +115,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// No-swizzle K-major matrix descriptor: 8-row x 16-byte core matrices, LBO = byte distance between the core
+// matrices of consecutive 16-byte K chunks, SBO = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
+    return d;                             // layout type 0 = no swizzle
+}
+
 // kind::f16 instruction descriptor: D=f32, A/B = f16 (fmt 0) or bf16 (fmt 1), both K-major.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);

@@ -33,12 +33,38 @@ __global__ void k0_stage_max(const float* __restrict__ cb, const int* __restrict
             mq[1] = 0.f;
             mq[2] = m;
             mq[3] = (float)Kv;
-            mq[4] = mq[5] = mq[6] = mq[7] = 0.f;
+            mq[4] = (float)gridDim.x;  // stages prepared: locates the norm slices behind the norms
+            mq[5] = mq[6] = mq[7] = 0.f;
         }
     }
 }
 
 // one warp per (stage, padded code row): fp16 operand row, scaled norm, running max of ||c||_2
+// Norm slice of a code (rvq_encode_tr.cu folds the norm into the MMA as one extra K = 16 step): 16 fp16 columns
+// {B1, B2, B3, PAD, 0...} with 2^11 B1 + 2 B2 + 2^-4 B3 = scaled norm exactly (three 11-bit pieces of the fp32
+// value) and PAD = 65504 for padding codes.  Stored per 128-code chunk in the canonical no-swizzle K-major UMMA
+// layout (8-row x 16-byte core matrices: row j, 16-byte K chunk kc at (j / 8) * 256 + kc * 128 + (j % 8) * 16).
+__device__ __forceinline__ void write_norm_slice(uint8_t* slices, int q, int Kpad, int k, float n, bool pad) {
+    uint8_t* chunk = slices + ((size_t)q * (Kpad / 128) + k / 128) * 4096;
+    const int j = k % 128;
+    uint8_t* p0 = chunk + (j / 8) * 256 + (j % 8) * 16;
+    float h1 = 0.f, h2 = 0.f, h3 = 0.f;
+    if (!pad) {
+        h1 = __uint_as_float(__float_as_uint(n) & 0xFFFFE000u);
+        const float rem = n - h1;
+        h2 = __uint_as_float(__float_as_uint(rem) & 0xFFFFE000u);
+        h3 = rem - h2;
+    }
+    const __half2 a = __floats2half2_rn(h1 * 4.8828125e-4f, h2 * 0.5f);
+    const __half2 b = __floats2half2_rn(h3 * 16.f, pad ? 65504.f : 0.f);
+    uint4 v;
+    v.x = *reinterpret_cast<const uint32_t*>(&a);
+    v.y = *reinterpret_cast<const uint32_t*>(&b);
+    v.z = v.w = 0u;
+    *reinterpret_cast<uint4*>(p0) = v;
+    *reinterpret_cast<uint4*>(p0 + 128) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad, int d, __half* __restrict__ op,
                            float* __restrict__ norm, float* __restrict__ meta) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -51,7 +77,10 @@ __global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad
     __half* orow = op + ((size_t)q * Kpad + k) * d;
     if (k >= Kv) {
         for (int i = lane; i < d; i += 32) orow[i] = __float2half_rn(0.f);
-        if (lane == 0) norm[(size_t)q * Kpad + k] = PAD_NORM;
+        if (lane == 0) {
+            norm[(size_t)q * Kpad + k] = PAD_NORM;
+            write_norm_slice(reinterpret_cast<uint8_t*>(norm + (size_t)nq * Kpad), q, Kpad, k, 0.f, true);
+        }
         return;
     }
     const float* crow = cb + ((size_t)q * K + k) * d;
@@ -65,6 +94,7 @@ __global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     if (lane == 0) {
         norm[(size_t)q * Kpad + k] = nrm * sb * sb;
+        write_norm_slice(reinterpret_cast<uint8_t*>(norm + (size_t)nq * Kpad), q, Kpad, k, nrm * sb * sb, false);
         // upper bound of ||c||_2 (fp32 summation slack) ; positive floats order like ints
         const float cn = sqrtf(nrm) * (1.f + 1e-5f);
         atomicMax(reinterpret_cast<int*>(mq + 1), __float_as_int(cn));
@@ -238,7 +268,8 @@ extern "C" int rvq_prepared_bytes(int nq, int K, int d, size_t* op_bytes, size_t
     }
     const size_t Kpad = round_up(K, CHUNK_N);
     if (op_bytes) *op_bytes = (size_t)nq * Kpad * d * sizeof(__half);
-    if (norm_bytes) *norm_bytes = (size_t)nq * Kpad * sizeof(float);
+    // scaled norms [nq, Kpad] fp32, then the fp16 norm slices [nq, Kpad / 128, 4096 bytes]
+    if (norm_bytes) *norm_bytes = (size_t)nq * Kpad * sizeof(float) + (size_t)nq * Kpad * 32;
     if (meta_bytes) *meta_bytes = (size_t)nq * META_STRIDE * sizeof(float);
     return RVQ_OK;
 }

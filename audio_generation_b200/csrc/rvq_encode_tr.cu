@@ -58,14 +58,16 @@ struct Params {
     float* stats_cnt;
     int num_tiles, nstage, nslots, pitch;  // pitch: floats per staging row (d + 4)
     int cluster;                           // CTAs per cluster sharing the codebook stream (TMA multicast)
-    uint32_t off_stg, off_rs, off_B, off_misc;  // A tiles (one per slot) at offset 0
+    uint32_t off_stg, off_B, off_misc;  // A tiles (one per slot) at offset 0
     unsigned long long* prof;              // [16] cycle / event counters (RVQ_PROFILE=1) or null
 };
 
 struct __align__(16) Misc {
     uint64_t full[MAX_RING], empty[MAX_RING], tmem_full[2], tmem_empty[2], norm_full[2], a_ready[2], scan_done[2];
     uint64_t stg_full[2], stg_free;
-    alignas(16) float norms[2][CH];  // 16-byte aligned (bulk-copy destination); scaled ||c||^2 of the chunk in each accumulator buffer (bulk-copied)
+    // norm term as one extra K = 16 MMA step, no-swizzle K-major operands (8-row x 16-byte core matrices):
+    alignas(128) uint8_t nslice[2][4096];   // B: norm slices of the chunk in each accumulator buffer (bulk-copied)
+    alignas(128) uint8_t a_extra[2][4096];  // A: per tile slot, row = {2^(a-b+11), 2^(a-b+1), 2^(a-b-4), 2^14, 0...}
     uint32_t tmem_base;
     float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
     float grp_best[2][2][TILE_M];   // [job parity][scan group][frame]: best score the group saw
@@ -86,7 +88,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_b = smem + p.off_B;
     float* staging = reinterpret_cast<float*>(smem + p.off_stg);
-    float* rstage_all = reinterpret_cast<float*>(smem + p.off_rs);
     Misc* misc = reinterpret_cast<Misc*>(smem + p.off_misc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,6 +122,8 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
         for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
         fence_mbar_init();
     }
+    for (int i = threadIdx.x; i < 2 * 4096 / 16; i += NUM_THREADS)
+        reinterpret_cast<uint4*>(&misc->a_extra[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_b);
     if (warp == 2) tmem_alloc<512>(&misc->tmem_base);
     tc_fence_before_sync();
@@ -168,6 +171,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             if (elect_one()) {
                 const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CH);
                 const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_b));
+                const int nq_prep = (int)p.cb_meta[4];  // stages prepared: the norm slices follow their norms
                 uint32_t g = 0, aphase = 0, st = 0, ph = 0;
                 long long t_aready = 0;
                 for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
@@ -178,14 +182,16 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     aphase ^= 1u << sl;
                     tc_fence_after_sync();
                     const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + (size_t)sl * a_tile_bytes));
-                    const float* nsrc = p.cb_norm + (size_t)(p.q_begin + job.q) * p.Kpad;
+                    const uint8_t* nsrc = reinterpret_cast<const uint8_t*>(p.cb_norm + (size_t)nq_prep * p.Kpad) +
+                                          (size_t)(p.q_begin + job.q) * n_chunks * 4096;
+                    const uint64_t adesc_x = umma_desc_nosw(smem_u32(misc->a_extra[sl]), 128, 256);
                     for (int c = 0; c < n_chunks; ++c, ++g) {
                         const uint32_t buf = g & 1, use = g >> 1;
                         mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
                         tc_fence_after_sync();
                         // the scan group has released this buffer: its norm slice can be replaced as well
-                        mbar_arrive_expect_tx(&misc->norm_full[buf], CH * 4);
-                        bulk_load_1d(misc->norms[buf], nsrc + c * CH, CH * 4, &misc->norm_full[buf]);
+                        mbar_arrive_expect_tx(&misc->norm_full[buf], 4096);
+                        bulk_load_1d(misc->nslice[buf], nsrc + (size_t)c * 4096, 4096, &misc->norm_full[buf]);
                         const uint32_t tmem_d = tmem_base + buf * CH;
                         uint64_t adesc = adesc0;
                         for (int ks = 0; ks < n_ks; ++ks) {
@@ -208,6 +214,10 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                                 ph ^= 1u;
                             }
                         }
+                        // the norm term: + A_extra . B_extra^T (see write_norm_slice in rvq_aux.cu)
+                        mbar_wait(&misc->norm_full[buf], use & 1);
+                        tc_fence_after_sync();
+                        umma_f16_ss(tmem_d, adesc_x, umma_desc_nosw(smem_u32(misc->nslice[buf]), 128, 256), idesc, 1);
                         umma_commit(&misc->tmem_full[buf]);
                     }
                 }
@@ -228,7 +238,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             long long t0 = clock64();
             mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);  // row constants of this job are visible
             aphase ^= 1u << sl;
-            const float na = misc->row_na[sl][my_row];
             const float delta = misc->row_delta[sl][my_row];
             float Cm[16];
 #pragma unroll
@@ -240,11 +249,9 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 if ((int)(g & 1) != grp) continue;
                 const long long tw0 = clock64();
                 mbar_wait(&misc->tmem_full[grp], (g >> 1) & 1);
-                mbar_wait(&misc->norm_full[grp], (g >> 1) & 1);
                 tc_fence_after_sync();
                 t_full += clock64() - tw0;
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CH;
-                const float* nptr = misc->norms[grp];
                 uint32_t va[16], vb[16];
                 tmem_ld_32x16(taddr, va);
                 uint32_t it = (uint32_t)c * (CH / 16);
@@ -252,10 +259,10 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 for (int cb = 0; cb < CH; cb += 32, it += 2) {
                     tmem_ld_wait();
                     tmem_ld_32x16(taddr + cb + 16, vb);
-                    scan16_2d(va, nptr + cb, na, it, Cm, m1, m2, m3, m4, nullptr);
+                    scan16_2d_raw(va, it, Cm, m1, m2, m3, m4, nullptr);
                     tmem_ld_wait();
                     if (cb + 32 < CH) tmem_ld_32x16(taddr + cb + 32, va);
-                    scan16_2d(vb, nptr + cb + 16, na, it + 1, Cm, m1, m2, m3, m4, nullptr);
+                    scan16_2d_raw(vb, it + 1, Cm, m1, m2, m3, m4, nullptr);
                 }
                 tc_fence_before_sync();
                 __syncwarp();
@@ -347,6 +354,18 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     *reinterpret_cast<uint4*>(base + ((((j0 + (uint32_t)j) << 4)) ^ rx)) = pk;
                 }
             };
+            // operand row of the norm term for a frame whose operand exponents are a (row) and b (codes)
+            constexpr int NORM_WINDOW_LO = -10;  // below: 2^(a-b-4) leaves the fp16 normal range -> exact scan
+            auto store_a_extra = [&](int a_, int b_) {
+                const int e = max(NORM_WINDOW_LO, min(ROW_OVER_CODE_MAX, a_ - b_));
+                const __half2 h01 = __floats2half2_rn(exp2i(e + 11), exp2i(e + 1));
+                const __half2 h23 = __floats2half2_rn(exp2i(e - 4), 16384.f);
+                uint4 v;
+                v.x = *reinterpret_cast<const uint32_t*>(&h01);
+                v.y = *reinterpret_cast<const uint32_t*>(&h23);
+                v.z = v.w = 0u;
+                *reinterpret_cast<uint4*>(misc->a_extra[s] + (row >> 3) * 256 + (row & 7) * 16) = v;
+            };
             // Coalesced asynchronous gather of one d-float row per frame of this warp into the staging buffer:
             // lane r's row number (index into `table`, rows of d floats; < 0 = none) is broadcast and the 32 lanes
             // copy 16 bytes each (d <= 128: one instruction per row).  Every thread then arrives on stg_full[s]
@@ -422,6 +441,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 const int b = ilog2f_floor(sb);
                 bool force_exact = !isfinite(sq);
                 const int a = pick_row_exp(amax, b, force_exact);
+                if (a - b < NORM_WINDOW_LO) force_exact = true;
                 const float sa = exp2i(a);
 #pragma unroll 1
                 for (int c0 = 0; c0 < d; c0 += 32) {
@@ -430,6 +450,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     tmem_ld_wait();
                     store_a(c0, v, sa);
                 }
+                store_a_extra(a, b);
                 float na, delta;
                 row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
                 misc->row_amax[s][row] = amax;
@@ -485,7 +506,8 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 }
                 // ---------------- exact scores, RS_ROWS entries per round: the frames expose their residual rows
                 // in shared memory and every 8-lane group re-scores the four candidates of one entry
-                float* rstage = rstage_all + (size_t)s * RS_ROWS * p.pitch;
+                // exposed rows live in this slot's A tile: its MMAs have retired, the next operand is written later
+                float* rstage = reinterpret_cast<float*>(a_tile);
                 float bs = __int_as_float(0x7f800000);
                 int kwin = 0x7fffffff;
                 int n_special = RS_ROWS, n_dirty = 0;  // read after the first barrier of round 0
@@ -620,7 +642,9 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     cnmax = mq[1];
                     b = ilog2f_floor(sb);
                     a = pick_row_exp(misc->row_amax[s][row] + p.cb_meta[(size_t)q_abs * META_STRIDE + 2], b, force_exact);
+                    if (a - b < NORM_WINDOW_LO) force_exact = true;
                     sa = exp2i(a);
+                    store_a_extra(a, b);
                 }
                 if (valid) {
                     p.idx[n * nq + q] = w;
@@ -843,9 +867,7 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     const uint32_t stg_bytes = (uint32_t)((TILE_M * p.pitch * 4 + 1023) / 1024 * 1024);
     const uint32_t misc_bytes = (uint32_t)((sizeof(tr::Misc) + 1023) / 1024 * 1024);
     p.off_stg = (uint32_t)p.nslots * a_bytes;
-    p.off_rs = p.off_stg + stg_bytes;
-    const uint32_t rs_bytes = (uint32_t)((2 * tr::RS_ROWS * p.pitch * 4 + 1023) / 1024 * 1024);
-    p.off_B = p.off_rs + rs_bytes;
+    p.off_B = p.off_stg + stg_bytes;
     const uint32_t fixed = p.off_B + misc_bytes + 1024;
     int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / tr::B_STAGE_BYTES) : 0;
     if (ns > tr::MAX_RING) ns = tr::MAX_RING;

@@ -47,8 +47,9 @@ int rvq_device_supported(int device);
 
 /* Sizes (HOST pointers out) of the derived codebook operands written by rvq_prepare_codebooks:
  *   op_bytes   : fp16 [nq, Kpad, d]  = -2 * 2^b_q * C_q            (UMMA B operand, K-major rows)
- *   norm_bytes : fp32 [nq, Kpad]     = 2^(2 b_q) * ||c||^2, padding codes = 2^100
- *   meta_bytes : fp32 [nq, 8]        = {2^b_q, max_k ||c_k||_2, max |c|, K_valid, 0...}       */
+ *   norm_bytes : fp32 [nq, Kpad]     = 2^(2 b_q) * ||c||^2, padding codes = 2^100; followed by the same norms
+ *                as fp16 UMMA operand slices [nq, Kpad/128, 4096 bytes] (three exact 11-bit pieces per code)
+ *   meta_bytes : fp32 [nq, 8]        = {2^b_q, max_k ||c_k||_2, max |c|, K_valid, nq prepared, 0...} */
 int rvq_prepared_bytes(int nq, int K, int d, size_t* op_bytes, size_t* norm_bytes, size_t* meta_bytes);
 
 /* K0. Derive the tensor-core operands from the fp32 master codebooks cb[nq, K, d].

@@ -35,7 +35,7 @@ def main():
     ref_op = (cb[0] * (-2.0 * sb)).half()
     print("prep op max diff", (op.reshape(nq, Kpad, d)[0, :K].float() - ref_op.float()).abs().max().item())
     ref_n = (cb[0] * cb[0]).sum(1) * sb * sb
-    print("prep norm rel diff", ((nrm.reshape(nq, Kpad)[0, :K] - ref_n).abs() / ref_n).max().item())
+    print("prep norm rel diff", ((nrm[:nq * Kpad].reshape(nq, Kpad)[0, :K] - ref_n).abs() / ref_n).max().item())
 
     # ---- single-stage filter scores
     x = torch.randn(128, d, device=dev)
@@ -47,7 +47,7 @@ def main():
     a_h = (x * rs[:, None]).half().float()
     b_h = op.reshape(nq, Kpad, d)[0].float()
     na = rs / sb
-    ref = a_h.double() @ b_h.double().t() + (na[:, None] * nrm.reshape(nq, Kpad)[0][None, :]).double()
+    ref = a_h.double() @ b_h.double().t() + (na[:, None] * nrm[:nq * Kpad].reshape(nq, Kpad)[0][None, :]).double()
     err = (scores.double() - ref).abs()
     print("scores nan:", torch.isnan(scores).sum().item(), "max abs err", err[:, :K].max().item(),
           "ref scale", ref[:, :K].abs().max().item())

@@ -303,7 +303,7 @@ def test_filter_scores_match_fp16_reference():
         sb = meta.reshape(2, 8)[1, 0]
         a_h = (x * rs[:, None]).half().double()
         b_h = op.reshape(2, Kpad, d)[1].double()
-        ref = a_h @ b_h.t() + ((rs / sb)[:, None] * nrm.reshape(2, Kpad)[1][None, :]).double()
+        ref = a_h @ b_h.t() + ((rs / sb)[:, None] * nrm[:2 * Kpad].reshape(2, Kpad)[1][None, :]).double()
         err = (scores.double() - ref).abs()[:, :K].max()
         assert not torch.isnan(scores[:, :K]).any()
         assert err <= 2e-6 * ref[:, :K].abs().max(), (K, d, float(err))
