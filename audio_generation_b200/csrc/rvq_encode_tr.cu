@@ -29,7 +29,11 @@
 namespace rvq {
 namespace tr {
 
-constexpr int CH = 128;  // codes per MMA / accumulator buffer
+#ifndef RVQ_TR_CH
+#define RVQ_TR_CH 128
+#endif
+constexpr int CH = RVQ_TR_CH;  // codes per MMA / accumulator buffer (64 or 128)
+constexpr uint32_t NSLICE_BYTES = CH * 32;  // norm slice of one chunk
 constexpr int SCAN_WARP0 = 4;
 constexpr int SCAN_THREADS = 256;
 constexpr int UPD_WARP0 = 12;
@@ -183,15 +187,15 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     tc_fence_after_sync();
                     const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + (size_t)sl * a_tile_bytes));
                     const uint8_t* nsrc = reinterpret_cast<const uint8_t*>(p.cb_norm + (size_t)nq_prep * p.Kpad) +
-                                          (size_t)(p.q_begin + job.q) * n_chunks * 4096;
+                                          (size_t)(p.q_begin + job.q) * n_chunks * NSLICE_BYTES;
                     const uint64_t adesc_x = umma_desc_nosw(smem_u32(misc->a_extra[sl]), 128, 256);
                     for (int c = 0; c < n_chunks; ++c, ++g) {
                         const uint32_t buf = g & 1, use = g >> 1;
                         mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
                         tc_fence_after_sync();
                         // the scan group has released this buffer: its norm slice can be replaced as well
-                        mbar_arrive_expect_tx(&misc->norm_full[buf], 4096);
-                        bulk_load_1d(misc->nslice[buf], nsrc + (size_t)c * 4096, 4096, &misc->norm_full[buf]);
+                        mbar_arrive_expect_tx(&misc->norm_full[buf], NSLICE_BYTES);
+                        bulk_load_1d(misc->nslice[buf], nsrc + (size_t)c * NSLICE_BYTES, NSLICE_BYTES, &misc->norm_full[buf]);
                         const uint32_t tmem_d = tmem_base + buf * CH;
                         uint64_t adesc = adesc0;
                         for (int ks = 0; ks < n_ks; ++ks) {

@@ -272,7 +272,7 @@ def main():
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s", frac=achieved / peaks["bf16"],
                     traffic=traffic, peak_source=peaks["source"] + " (burst bf16 cuBLAS 8192^3)",
                     frac_of_sustained=achieved / peaks["bf16_sustained"], frac_of_spec=achieved / SPEC_BF16_TFLOPS,
-                    kernel="rvq_encode_tc_kernel", flops_per_frame=flops_per_frame,
+                    kernel="rvq_encode_tr_kernel" if d <= 128 else "rvq_encode_tc_kernel", flops_per_frame=flops_per_frame,
                     note="algorithmic flops = nq*2*K*d per frame (distance GEMM only)")
     cpu = None
     if not args.no_cpu and world == 1:
