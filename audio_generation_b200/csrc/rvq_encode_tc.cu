@@ -166,7 +166,12 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
         float* ssum = (p.stats_sum && row_valid) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d : nullptr;
         int c0 = sub * 4;
 #pragma unroll 1
-        for (; c0 + 128 <= d + sub * 4; c0 += 128) apply_seg<4>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
+        // 256 features per step when possible: one L2 round trip covers eight pieces of the frame and of the code
+        for (; c0 + 256 <= d + sub * 4; c0 += 256) apply_seg<8>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
+        if (d & 128) {
+            apply_seg<4>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
+            c0 += 128;
+        }
         if (d & 64) apply_seg<2>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
     }
 #pragma unroll
