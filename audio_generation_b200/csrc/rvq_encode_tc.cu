@@ -53,6 +53,7 @@ struct EncParams {
     float* stats_cnt;
     float* r_scratch;  // per-CTA [128, d] fp32 when the residual tile does not fit in shared memory
     int num_tiles, nstage, nslots, r_pitch;
+    int cluster;  // CTAs per cluster sharing the codebook stream (TMA multicast)
     uint32_t off_B, off_misc;  // A tiles (one per slot) at offset 0
     float* dbg_scores;                // [128, Kpad] (bring-up hook) or null
     float* dbg_rowscale;              // [128] or null
@@ -332,13 +333,17 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     const int n_chunks = p.Kpad / CHUNK_N;
     const int nstage = p.nstage;
     const uint32_t a_tile_bytes = (uint32_t)n_ks * A_SLICE_BYTES;
-    const int n_local = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // every CTA of a cluster walks the same job sequence (tiles past the end are empty: all frames invalid)
+    const int n_local = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int CL = p.cluster;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
     const int nslots = p.nslots;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < nstage; ++i) {
             mbar_init(&misc->full[i], 1);
-            mbar_init(&misc->empty[i], 1);
+            mbar_init(&misc->empty[i], (uint32_t)CL);  // one tcgen05.commit arrive per CTA of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&misc->tmem_full[i], 1);
@@ -356,6 +361,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     if (warp == 2) tmem_alloc<512>(&misc->tmem_base);
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // the peers' barriers are initialised before anything is multicast to them
     tc_fence_after_sync();
     const uint32_t tmem_base = misc->tmem_base;
 
@@ -367,62 +373,80 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     if (warp < SCAN_WARP0) reg_dealloc<40>();
     if (warp == 0) {
         // =========================================================== TMA producer (codebook slices)
-        if (lane == 0) {
-            uint32_t it = 0;
+        if (elect_one()) {
+            uint32_t st = 0, ph = 0;
+            const uint32_t part_bytes = B_STAGE_BYTES / (uint32_t)CL;
+            const int part_rows = CHUNK_N / CL;
             for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
-                const int row0 = (p.q_begin + job.q) * p.Kpad;
+                const int row0 = (p.q_begin + job.q) * p.Kpad + (int)crank * part_rows;
                 for (int c = 0; c < n_chunks; ++c) {
-                    for (int ks = 0; ks < n_ks; ++ks, ++it) {
-                        const uint32_t s = it % nstage, ph = (it / nstage) & 1;
-                        mbar_wait(&misc->empty[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&misc->full[s], B_STAGE_BYTES);
-                        tma_load_2d(smem_b + (size_t)s * B_STAGE_BYTES, &tmap_b, &misc->full[s], ks * KSLICE,
-                                    row0 + c * CHUNK_N);
+                    for (int ks = 0; ks < n_ks; ++ks) {
+                        mbar_wait(&misc->empty[st], ph ^ 1);  // every CTA of the cluster has consumed the slot
+                        mbar_arrive_expect_tx(&misc->full[st], B_STAGE_BYTES);
+                        uint8_t* dst = smem_b + (size_t)st * B_STAGE_BYTES + crank * part_bytes;
+                        if (CL > 1)  // my 1/CL of the slice goes to every CTA of the cluster
+                            tma_load_2d_mc(dst, &tmap_b, &misc->full[st], ks * KSLICE, row0 + c * CHUNK_N, cmask);
+                        else
+                            tma_load_2d(dst, &tmap_b, &misc->full[st], ks * KSLICE, row0 + c * CHUNK_N);
+                        if (++st == (uint32_t)nstage) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
                     }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // =========================================================== MMA issuer
-        const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CHUNK_N);
-        uint32_t it = 0, g = 0, aphase = 0;
-        for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
-            const int sl = job.slot % nslots;
-            mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);
-            aphase ^= 1u << sl;
-            tc_fence_after_sync();
-            const uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
-            for (int c = 0; c < n_chunks; ++c, ++g) {
-                const uint32_t buf = g & 1, use = g >> 1;
-                mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
+        // ONE elected thread runs the whole loop: a lone warp pays ~8 cycles of latency per instruction, so the
+        // issue loop stays at a handful of instructions per MMA (no divisions, no per-iteration warp syncs,
+        // descriptors advanced by additions; elect.sync keeps ptxas from wrapping every MMA in a waterfall loop).
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CHUNK_N);
+            const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_b));
+            uint32_t g = 0, aphase = 0, st = 0, ph = 0;
+            for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+                const int sl = job.slot % nslots;
+                mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);
+                aphase ^= 1u << sl;
                 tc_fence_after_sync();
-                if (lane == 0) {
+                const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + (size_t)sl * a_tile_bytes));
+                const float* nsrc = p.cb_norm + (size_t)(p.q_begin + job.q) * p.Kpad;
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const uint32_t buf = g & 1, use = g >> 1;
+                    mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
+                    tc_fence_after_sync();
                     // the scan group has released this buffer: its norm slice can be replaced as well
                     mbar_arrive_expect_tx(&misc->norm_full[buf], CHUNK_N * 4);
-                    bulk_load_1d(misc->norms[buf], p.cb_norm + (size_t)(p.q_begin + job.q) * p.Kpad + c * CHUNK_N,
-                                 CHUNK_N * 4, &misc->norm_full[buf]);
-                }
-                const uint32_t tmem_d = tmem_base + buf * CHUNK_N;
-                for (int ks = 0; ks < n_ks; ++ks, ++it) {
-                    const uint32_t s = it % nstage, ph = (it / nstage) & 1;
-                    mbar_wait(&misc->full[s], ph);
-                    tc_fence_after_sync();
-                    if (lane == 0) {
-                        const uint64_t adesc = umma_desc_sw128(smem_u32(a_tile + (size_t)ks * A_SLICE_BYTES));
-                        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + (size_t)s * B_STAGE_BYTES));
-#pragma unroll
-                        for (int k16 = 0; k16 < KSLICE / 16; ++k16) {
-                            // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
-                            umma_f16_ss(tmem_d, adesc + (uint64_t)(k16 * 2), bdesc + (uint64_t)(k16 * 2), idesc,
-                                        (ks | k16) != 0);
+                    bulk_load_1d(misc->norms[buf], nsrc + c * CHUNK_N, CHUNK_N * 4, &misc->norm_full[buf]);
+                    const uint32_t tmem_d = tmem_base + buf * CHUNK_N;
+                    uint64_t adesc = adesc0;
+                    for (int ks = 0; ks < n_ks; ++ks) {
+                        mbar_wait(&misc->full[st], ph);
+                        tc_fence_after_sync();
+                        const uint64_t bdesc = bdesc0 + (uint64_t)(st * (B_STAGE_BYTES >> 4));
+                        // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
+                        umma_f16_ss(tmem_d, adesc, bdesc, idesc, ks != 0);
+                        umma_f16_ss(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
+                        umma_f16_ss(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
+                        umma_f16_ss(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
+                        // frees the ring slot (in every CTA of the cluster) when these MMAs retire
+                        if (CL > 1)
+                            umma_commit_mc(&misc->empty[st], cmask);
+                        else
+                            umma_commit(&misc->empty[st]);
+                        adesc += (uint64_t)(A_SLICE_BYTES >> 4);
+                        if (++st == (uint32_t)nstage) {
+                            st = 0;
+                            ph ^= 1u;
                         }
-                        umma_commit(&misc->empty[s]);  // frees the ring slot when these MMAs retire
-                        if (ks == n_ks - 1) umma_commit(&misc->tmem_full[buf]);
                     }
-                    __syncwarp();
+                    umma_commit(&misc->tmem_full[buf]);
                 }
             }
         }
+        __syncwarp();
     } else if (warp < SCAN_WARP0) {
     } else if (warp < UPD_WARP0) {
         reg_dealloc<88>();
@@ -774,6 +798,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
 
     tc_fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
     if (warp == 2) {
         tc_fence_after_sync();
         tmem_dealloc<512>(tmem_base);
@@ -862,7 +887,11 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nq_total * Kpad};
     const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)CHUNK_N};
+    // Codebook multicast across a cluster is available here too (RVQ_CLUSTER_TC=2|4) but measured slower for
+    // this kernel (C4 shape: 5.5 -> 3.1 M frames/s: a slow exact scan in one CTA stalls its whole cluster).
+    static const int cluster_env = getenv("RVQ_CLUSTER_TC") ? atoi(getenv("RVQ_CLUSTER_TC")) : 1;
+    const int CL = dbg_scores ? 1 : ((cluster_env == 1 || cluster_env == 2 || cluster_env == 4) ? cluster_env : 1);
+    const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)(CHUNK_N / CL)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(cb_op), gdim, gstride, box,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -872,8 +901,11 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
         return RVQ_ERR_CUDA;
     }
     const int num_tiles = (int)((N + TILE_M - 1) / TILE_M);
-    const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+    // persistent grid of whole clusters: as many as the tiles need, at most one CTA per SM
+    const int want_clusters = (num_tiles + CL - 1) / CL, max_clusters = num_sms / CL;
+    const int grid = (want_clusters < max_clusters ? want_clusters : max_clusters) * CL;
     EncParams p{};
+    p.cluster = CL;
     p.x = x;
     p.N = N;
     p.ad = RowAddrT{L, sb, sl, sd};
@@ -913,14 +945,26 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
         }
         p.r_scratch = reinterpret_cast<float*>(base);
     }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = sp.total;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (dbg_scores) {
         RVQ_CUDA(cudaFuncSetAttribute(rvq_encode_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sp.total));
-        rvq_encode_tc_kernel<true><<<grid, NUM_THREADS, sp.total, st>>>(tmap, p);
+        RVQ_CUDA(cudaLaunchKernelEx(&cfg, rvq_encode_tc_kernel<true>, tmap, p));
     } else {
         RVQ_CUDA(cudaFuncSetAttribute(rvq_encode_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sp.total));
-        rvq_encode_tc_kernel<false><<<grid, NUM_THREADS, sp.total, st>>>(tmap, p);
+        RVQ_CUDA(cudaLaunchKernelEx(&cfg, rvq_encode_tc_kernel<false>, tmap, p));
     }
     RVQ_CUDA(cudaGetLastError());
     return RVQ_OK;
