@@ -187,6 +187,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+// registers -> TMEM: 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 1-D bulk copy shared -> global (bytes multiple of 16, both 16-byte aligned), tracked by the bulk async-group
@@ -260,6 +269,15 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
+}
+// 16 consecutive floats (64 bytes, 32-byte aligned) of global memory -> registers with two 256-bit loads
+__device__ __forceinline__ void ldg_nc_16f(const float* p, uint32_t (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[8 * i + 0]), "=r"(v[8 * i + 1]), "=r"(v[8 * i + 2]), "=r"(v[8 * i + 3]), "=r"(v[8 * i + 4]),
+                       "=r"(v[8 * i + 5]), "=r"(v[8 * i + 6]), "=r"(v[8 * i + 7])
+                     : "l"(p + 8 * i));
 }
 __device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
     float4 r;

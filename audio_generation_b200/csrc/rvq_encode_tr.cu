@@ -87,6 +87,9 @@ struct __align__(16) Misc {
     double commit_acc[MAX_NQ];
 };
 
+// kStats: EMA statistics requested (compile-time so that each instantiation carries one apply path only: the
+// update threads are register-bound)
+template <bool kStats>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -472,9 +475,13 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 release();
                 mbar_arrive(&misc->a_ready[s]);
             }
-            for (JobIter job(n_local, nq, nslots); job.valid(); job.next(), ++ticket) {
+            constexpr bool stats = kStats;
+            // a job takes a turn at the staging buffer only if it uses it: EMA statistics (the bulk reduction reads
+            // the residual rows from shared memory) or the last stage (x / xq rows, next tile)
+            for (JobIter job(n_local, nq, nslots); job.valid(); ticket += (stats || job.q + 1 == nq) ? 1 : 0, job.next()) {
                 if (job.slot % nslots != s) continue;
                 const int q = job.q, q_abs = p.q_begin + q;
+                const bool staged = stats || q + 1 == nq;
                 const int tile = blockIdx.x + job.i * gridDim.x;
                 const long long n = (long long)tile * TILE_M + row;
                 const bool valid = n < p.N;
@@ -632,8 +639,18 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     misc->n_dirty[s] = 0;
                 }
                 const long long tj2 = clock64();
-                acquire(ticket);
-                gather_codes(cbq, w);
+                // the selected code vector: with statistics it goes through the staging buffer (whose row then
+                // becomes the source of the bulk reduction); without, my thread reads its 4d bytes straight into
+                // registers with 256-bit loads, two 32-feature pieces ahead of their use
+                const float* crow = cbq + (size_t)w * d;
+                uint32_t ca[kStats ? 1 : 16], cb_[kStats ? 1 : 16];
+                if (staged) acquire(ticket);
+                if constexpr (kStats) {
+                    gather_codes(cbq, w);
+                } else {
+                    ldg_nc_16f(crow, ca);
+                    ldg_nc_16f(crow + 16, cb_);
+                }
                 const long long tj3 = clock64();
                 // ---------------- constants of the next stage's operand (scale chosen from a bound known now)
                 const bool write_a = next_q_abs >= 0;
@@ -654,8 +671,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     p.idx[n * nq + q] = w;
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + w, 1.f);
                 }
-                const bool stats = p.stats_sum != nullptr;
-                wait_staging();  // the selected code vectors have landed
+                if constexpr (kStats) wait_staging();  // the selected code vectors have landed
                 const long long tj4 = clock64();
                 // ---------------- r <- r - c (fp32, tensor memory), next operand row, statistics row
                 float sq = 0.f;
@@ -681,7 +697,35 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     tmem_st_32x32(t_r + c0, v);
                     if (write_a) store_a(c0, v, sa);
                 };
-                {
+                // 16 features of my frame with the code vector piece in registers
+                auto apply16r = [&](uint32_t (&v)[16], const uint32_t (&c)[kStats ? 1 : 16], int c0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float nf = __uint_as_float(v[j]) - __uint_as_float(c[kStats ? 0 : j]);
+                        sq = fmaf(nf, nf, sq);
+                        v[j] = __float_as_uint(nf);
+                    }
+                    tmem_st_32x16(t_r + c0, v);
+                    if (write_a) {
+                        uint8_t* base = a_row + (uint32_t)(c0 >> 6) * A_SLICE_BYTES;
+                        const uint32_t j0 = ((uint32_t)c0 >> 3) & 7u;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint4 pk;
+                            __half2 hh;
+                            hh = __floats2half2_rn(__uint_as_float(v[8 * j + 0]) * sa, __uint_as_float(v[8 * j + 1]) * sa);
+                            pk.x = *reinterpret_cast<const uint32_t*>(&hh);
+                            hh = __floats2half2_rn(__uint_as_float(v[8 * j + 2]) * sa, __uint_as_float(v[8 * j + 3]) * sa);
+                            pk.y = *reinterpret_cast<const uint32_t*>(&hh);
+                            hh = __floats2half2_rn(__uint_as_float(v[8 * j + 4]) * sa, __uint_as_float(v[8 * j + 5]) * sa);
+                            pk.z = *reinterpret_cast<const uint32_t*>(&hh);
+                            hh = __floats2half2_rn(__uint_as_float(v[8 * j + 6]) * sa, __uint_as_float(v[8 * j + 7]) * sa);
+                            pk.w = *reinterpret_cast<const uint32_t*>(&hh);
+                            *reinterpret_cast<uint4*>(base + ((((j0 + (uint32_t)j) << 4)) ^ rx)) = pk;
+                        }
+                    }
+                };
+                if constexpr (kStats) {
                     // two 32-feature pieces in flight: the next TMEM load is issued before the current piece is used
                     uint32_t va[32], vb[32];
                     tmem_ld_32x32(t_r, va);
@@ -693,6 +737,25 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                         tmem_ld_wait();
                         if (c0 + 64 < d) tmem_ld_32x32(t_r + c0 + 64, va);
                         apply32(vb, c0 + 32);
+                    }
+                } else {
+                    // 16-feature pieces: TMEM load one piece ahead, code loads two pieces ahead
+                    uint32_t va[16], vb[16];
+                    tmem_ld_32x16(t_r, va);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < d; c0 += 32) {
+                        tmem_ld_wait();
+                        tmem_ld_32x16(t_r + c0 + 16, vb);
+                        apply16r(va, ca, c0);
+                        if constexpr (!kStats) {
+                            if (c0 + 32 < d) ldg_nc_16f(crow + c0 + 32, ca);
+                        }
+                        tmem_ld_wait();
+                        if (c0 + 32 < d) tmem_ld_32x16(t_r + c0 + 32, va);
+                        apply16r(vb, cb_, c0 + 16);
+                        if constexpr (!kStats) {
+                            if (c0 + 32 < d) ldg_nc_16f(crow + c0 + 48, cb_);
+                        }
                     }
                 }
                 if (stats) {
@@ -722,7 +785,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 const long long tj5 = clock64();
                 if (write_a) {
                     fence_proxy_async_smem();
-                    release();
+                    if (staged) release();
                     mbar_arrive(&misc->a_ready[s]);
                 } else {
                     // ---------------- last stage: xq = x - final residual, then the slot takes its next tile
@@ -927,7 +990,8 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
         p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 256) & ~(size_t)7));
         RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 256, st));
     }
-    RVQ_CUDA(cudaFuncSetAttribute(tr::rvq_encode_tr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
+    auto kern = stats_sum ? tr::rvq_encode_tr_kernel<true> : tr::rvq_encode_tr_kernel<false>;
+    RVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(tr::NUM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem_total;
@@ -944,14 +1008,14 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     cfg.gridDim = dim3((unsigned)(max_clusters * CL), 1, 1);
     {
         int nc = 0;
-        if (cudaOccupancyMaxActiveClusters(&nc, tr::rvq_encode_tr_kernel, &cfg) == cudaSuccess && nc > 0 && nc < max_clusters)
+        if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc > 0 && nc < max_clusters)
             max_clusters = nc;
         (void)cudaGetLastError();
     }
     const int want_clusters = (num_tiles + CL - 1) / CL;
     const int grid = (want_clusters < max_clusters ? want_clusters : max_clusters) * CL;
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    RVQ_CUDA(cudaLaunchKernelEx(&cfg, tr::rvq_encode_tr_kernel, tmap, p));
+    RVQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, p));
     RVQ_CUDA(cudaGetLastError());
     return RVQ_OK;
 }
