@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RVQ_ABI_VERSION 3
+#define RVQ_ABI_VERSION 4
 
 typedef enum {
     RVQ_OK = 0,

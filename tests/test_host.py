@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.rvq_version() == 3
+    assert lib.rvq_version() == 4
 
 
 def test_argument_checks_need_no_gpu():
@@ -27,7 +27,8 @@ def test_argument_checks_need_no_gpu():
     lib = _lib.load()
     ob, nb, mb = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
     assert lib.rvq_prepared_bytes(8, 1000, 128, ctypes.byref(ob), ctypes.byref(nb), ctypes.byref(mb)) == 0
-    assert ob.value == 8 * 1024 * 128 * 2 and nb.value == 8 * 1024 * 4 and mb.value == 8 * 8 * 4
+    # norms: fp32 [nq, Kpad] followed by their fp16 operand slices (32 bytes per code)
+    assert ob.value == 8 * 1024 * 128 * 2 and nb.value == 8 * 1024 * (4 + 32) and mb.value == 8 * 8 * 4
     assert lib.rvq_prepared_bytes(0, 1, 1, None, None, None) == -1
     assert b"positive" in lib.rvq_last_error()
     n = ctypes.c_size_t()
