@@ -75,6 +75,8 @@ struct __align__(16) Misc {
     uint32_t tmem_base;
     float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
     float grp_best[2][2][TILE_M];   // [job parity][scan group][frame]: best score the group saw
+    uint16_t wbest[2][2][TILE_M];   // [slot][scan group][frame]: the code that scored it (approximate argmin)
+    float vbest[2][2][TILE_M];      // [slot][scan group][frame]: that score
     uint32_t g_rows[2][2][TILE_M];  // [slot][group][frame]: loads that may hold a candidate
     uint16_t g_cols[2][2][TILE_M];  // [slot][group][frame]: columns that may hold a candidate
     int win[2][TILE_M];             // [slot][frame]: selected code
@@ -281,6 +283,15 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             for (int j = 3; j < 15; j += 2) vb_ = fminf(fminf(vb_, Cm[j]), Cm[j + 1]);
             vb_ = fminf(vb_, Cm[15]);
             misc->grp_best[jpar][grp][my_row] = vb_;
+            {
+                // the code behind the group's best score: the load of the smallest load minimum, the first column
+                // that attains the column minimum
+                int jmin = 15;
+#pragma unroll
+                for (int j = 14; j >= 0; --j) jmin = (Cm[j] == vb_) ? j : jmin;
+                misc->wbest[sl][grp][my_row] = (uint16_t)((__float_as_uint(m1) & IT_MASK) * 16u + (uint32_t)jmin);
+                misc->vbest[sl][grp][my_row] = vb_;
+            }
             named_bar_sync(BAR_SCAN, SCAN_THREADS);
             {
                 const float best = fminf(vb_, misc->grp_best[jpar][grp ^ 1][my_row]);
@@ -637,6 +648,12 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 if (gw == 0 && lane == 0) {  // next use is after the next scan of this slot
                     misc->n_special[s] = 0;
                     misc->n_dirty[s] = 0;
+                }
+                if (p.prof) {
+                    const int w_spec = misc->vbest[s][0][row] <= misc->vbest[s][1][row] ? misc->wbest[s][0][row]
+                                                                                        : misc->wbest[s][1][row];
+                    const unsigned miss = __ballot_sync(0xffffffffu, valid && w_spec != w);
+                    if (lane == 0 && miss) atomicAdd(p.prof + 20, (unsigned long long)__popc(miss));
                 }
                 const long long tj2 = clock64();
                 // the selected code vector: with statistics it goes through the staging buffer (whose row then

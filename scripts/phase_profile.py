@@ -46,6 +46,7 @@ if d <= 128 and os.environ.get("RVQ_KERNEL") != "tc":
     print(f"  rerank split: classify+barrier={prof[13]/n:.0f} expose-rows+barrier={prof[14]/n:.0f} score={prof[15]/n:.0f}")
     print(f"  control warps per tile-stage: producer waits for a free ring slot={prof[16]/n:.0f}  MMA waits for codebook data={prof[17]/n:.0f} "
           f"for the operand (a_ready)={prof[18]/n:.0f} for a free accumulator={prof[19]/n:.0f}")
+    print(f"frames whose exact winner differs from the approximate argmin, per tile-stage: {prof[20]/n:.3f}")
     print(f"dirty rows per tile-stage={prof[4]/n:.3f}  multi-candidate rows per tile-stage={prof[6]/n:.2f}")
     sys.exit(0)
 print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+wait {prof[1]/n:.0f})  update={prof[2]/n:.0f} "
