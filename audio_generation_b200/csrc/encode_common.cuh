@@ -60,6 +60,7 @@ __device__ __forceinline__ int pick_row_exp(float amax_bound, int b, bool& force
 // Candidate set of one scan group for one frame, factorised: up to three loads (`it`, 9 bits each) x a 16-bit
 // column mask.  bits 27-28 = number of loads, bit 31 = OVER (more loads than kept, or no usable filter result).
 constexpr uint32_t G_OVER = 0x80000000u;
+constexpr uint32_t G_NOFILTER = 0x40000000u;  // no usable filter result at all (NaN / overflow / forced exact)
 
 
 // ---------------------------------------------------------------------------------------------------------

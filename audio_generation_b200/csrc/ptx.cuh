@@ -279,6 +279,23 @@ __device__ __forceinline__ void ldg_nc_16f(const float* p, uint32_t (&v)[16]) {
                        "=r"(v[8 * i + 5]), "=r"(v[8 * i + 6]), "=r"(v[8 * i + 7])
                      : "l"(p + 8 * i));
 }
+// 32 consecutive floats (128 bytes, 32-byte aligned) of global memory <- / -> registers with four 256-bit accesses
+__device__ __forceinline__ void ldg_nc_32f(const float* p, uint32_t (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[8 * i + 0]), "=r"(v[8 * i + 1]), "=r"(v[8 * i + 2]), "=r"(v[8 * i + 3]), "=r"(v[8 * i + 4]),
+                       "=r"(v[8 * i + 5]), "=r"(v[8 * i + 6]), "=r"(v[8 * i + 7])
+                     : "l"(p + 8 * i));
+}
+__device__ __forceinline__ void stg_32f(float* p, const uint32_t (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p + 8 * i), "r"(v[8 * i + 0]),
+                     "r"(v[8 * i + 1]), "r"(v[8 * i + 2]), "r"(v[8 * i + 3]), "r"(v[8 * i + 4]), "r"(v[8 * i + 5]),
+                     "r"(v[8 * i + 6]), "r"(v[8 * i + 7])
+                     : "memory");
+}
 __device__ __forceinline__ float4 ldg_nc_v4(const float* p) {
     float4 r;
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));

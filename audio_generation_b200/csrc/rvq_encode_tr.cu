@@ -77,10 +77,14 @@ struct __align__(16) Misc {
     float grp_best[2][2][TILE_M];   // [job parity][scan group][frame]: best score the group saw
     uint16_t wbest[2][2][TILE_M];   // [slot][scan group][frame]: the code that scored it (approximate argmin)
     float vbest[2][2][TILE_M];      // [slot][scan group][frame]: that score
-    uint32_t g_rows[2][2][TILE_M];  // [slot][group][frame]: loads that may hold a candidate
-    uint16_t g_cols[2][2][TILE_M];  // [slot][group][frame]: columns that may hold a candidate
+    // candidate sets, double buffered by stage parity: the verification of stage q may still read them while the
+    // scan of stage q + 1 writes
+    uint32_t g_rows[2][2][2][TILE_M];  // [slot][stage parity][group][frame]: loads that may hold a candidate
+    uint16_t g_cols[2][2][2][TILE_M];  // [slot][stage parity][group][frame]: columns that may hold a candidate
     int win[2][TILE_M];             // [slot][frame]: selected code
-    int n_special[2], n_dirty[2];
+    int n_special[2], n_dirty[2], n_srows[2], n_hard[2];
+    uint8_t pos_of[2][TILE_M];   // [slot][frame]: its row in the verification buffer
+    uint8_t repair[2][TILE_M];   // [slot][frame]: the last stage's winner was corrected after the operand went out
     uint32_t pairs[2][RS_ROWS * 4];      // [slot][entry * 4 + t]: code scored
     float pair_score[2][RS_ROWS * 4];    // its exact score
     uint16_t special_rows[2][4 * TILE_M];  // [slot][entry]: frame | block << 8 | 0x8000 if it needs the exact scan
@@ -89,9 +93,13 @@ struct __align__(16) Misc {
     double commit_acc[MAX_NQ];
 };
 
+#include "tr_update_spec.cuh"
+
 // kStats: EMA statistics requested (compile-time so that each instantiation carries one apply path only: the
 // update threads are register-bound)
-template <bool kStats>
+// kSpec (only without statistics): speculative update with exact verification behind the next stage
+// (tr_update_spec.cuh; RVQ_SPEC=1).  Bit-identical results; measured slower on C2, kept selectable.
+template <bool kStats, bool kSpec>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -126,6 +134,8 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             mbar_init(&misc->stg_full[i], GRP_THREADS);
             misc->n_special[i] = 0;
             misc->n_dirty[i] = 0;
+            misc->n_srows[i] = 0;
+            misc->n_hard[i] = 0;
         }
         mbar_init(&misc->stg_free, GRP_THREADS);
         for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
@@ -309,9 +319,10 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 for (int j = 0; j < 16; ++j) cols |= (Cm[j] <= T) ? (1u << j) : 0u;
                 if (nofilter) cols = 0xFFFFu;
                 const uint32_t rows = (__float_as_uint(m1) & IT_MASK) | ((__float_as_uint(m2) & IT_MASK) << 9) |
-                                      ((__float_as_uint(m3) & IT_MASK) << 18) | (nr << 27) | (over ? G_OVER : 0u);
-                misc->g_rows[sl][grp][my_row] = rows;
-                misc->g_cols[sl][grp][my_row] = (uint16_t)cols;
+                                      ((__float_as_uint(m3) & IT_MASK) << 18) | (nr << 27) | (over ? G_OVER : 0u) |
+                                      (nofilter ? G_NOFILTER : 0u);
+                misc->g_rows[sl][job.q & 1][grp][my_row] = rows;
+                misc->g_cols[sl][job.q & 1][grp][my_row] = (uint16_t)cols;
             }
             mbar_arrive(&misc->scan_done[sl]);
             t_scan += clock64() - t1;
@@ -327,7 +338,10 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
         const int s = (warp - UPD_WARP0) >> 2;    // tile slot served by this group
         const int row = (warp & 3) * 32 + lane;   // frame of the tile = TMEM lane (UPD_WARP0 % 4 == 0)
         const int gw = warp & 3;                  // warp inside the group
-        if (s < nslots) {
+        if constexpr (kSpec) {
+            // speculative update, exact verification behind the next stage (tr_update_spec.cuh)
+            update_group_spec(p, misc, smem, staging, tmem_base, warp, lane, n_local);
+        } else if (s < nslots) {
             const uint32_t t_r = tmem_base + ((uint32_t)(gw * 32) << 16) + TMEM_RES_COL + (uint32_t)(s * d);
             float* stg_row = staging + (size_t)row * p.pitch;
             float* stg_warp = staging + (size_t)(gw * 32) * p.pitch;  // first staging row of this warp's frames
@@ -505,8 +519,8 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 const long long tj1 = clock64();
                 // ---------------- classify my frame: certified (one candidate), several candidates, exact scan.
                 // A frame with nc candidates takes ceil(nc / 4) re-rank entries (four candidates per entry).
-                const uint32_t r0 = misc->g_rows[s][0][row], r1 = misc->g_rows[s][1][row];
-                const uint32_t c0m = misc->g_cols[s][0][row], c1m = misc->g_cols[s][1][row];
+                const uint32_t r0 = misc->g_rows[s][q & 1][0][row], r1 = misc->g_rows[s][q & 1][1][row];
+                const uint32_t c0m = misc->g_cols[s][q & 1][0][row], c1m = misc->g_cols[s][q & 1][1][row];
                 const int n0 = (int)((r0 >> 27) & 3u) * __popc(c0m), n1 = (int)((r1 >> 27) & 3u) * __popc(c1m);
                 const int nc = n0 + n1;
                 int w = 0, mypos = -1, myk = 0;
@@ -566,8 +580,8 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                         const int ent = slot16 < n_round ? misc->special_rows[s][base + slot16] : 0x8000;
                         if (__any_sync(0xffffffffu, !(ent & 0x8000))) {
                             const int rr = ent & 0x7f, blk = (ent >> 8) & 0x7f;
-                            const CandSet cs(misc->g_rows[s][0][rr], misc->g_cols[s][0][rr], misc->g_rows[s][1][rr],
-                                             misc->g_cols[s][1][rr]);
+                            const CandSet cs(misc->g_rows[s][q & 1][0][rr], misc->g_cols[s][q & 1][0][rr], misc->g_rows[s][q & 1][1][rr],
+                                             misc->g_cols[s][q & 1][1][rr]);
                             // the frame's row sits at its first entry of this round
                             const int first = max(slot16 - blk, 0);
                             const float* rrow = rstage + (size_t)first * p.pitch;
@@ -616,7 +630,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                             const int ent = misc->special_rows[s][base + i];
                             if (!(ent & 0x8000)) continue;
                             const int rr = ent & 0x7f;
-                            uint32_t cols = (uint32_t)misc->g_cols[s][0][rr] | (uint32_t)misc->g_cols[s][1][rr];
+                            uint32_t cols = (uint32_t)misc->g_cols[s][q & 1][0][rr] | (uint32_t)misc->g_cols[s][q & 1][1][rr];
                             if (cols == 0) cols = 0xFFFFu;
                             const int n_it = (Kv + 15) / 16, per_w = (n_it + 3) / 4;
                             const int it0 = min(n_it, gw * per_w), it1 = min(n_it, it0 + per_w);
@@ -948,7 +962,11 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     p.nslots = 2;
     p.pitch = d + 4;
     const uint32_t a_bytes = (uint32_t)(d / KSLICE) * A_SLICE_BYTES;
-    const uint32_t stg_bytes = (uint32_t)((TILE_M * p.pitch * 4 + 1023) / 1024 * 1024);
+    static const bool spec_env = getenv("RVQ_SPEC") && atoi(getenv("RVQ_SPEC")) != 0;
+    const bool spec = spec_env && !stats_sum;
+    // staging buffer of one tile, or (speculative update) the verification row buffers of the two slots
+    const int stg_rows = spec ? 2 * tr::RS_CAP : TILE_M;
+    const uint32_t stg_bytes = (uint32_t)((stg_rows * p.pitch * 4 + 1023) / 1024 * 1024);
     const uint32_t misc_bytes = (uint32_t)((sizeof(tr::Misc) + 1023) / 1024 * 1024);
     p.off_stg = (uint32_t)p.nslots * a_bytes;
     p.off_B = p.off_stg + stg_bytes;
@@ -1007,7 +1025,8 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
         p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 256) & ~(size_t)7));
         RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 256, st));
     }
-    auto kern = stats_sum ? tr::rvq_encode_tr_kernel<true> : tr::rvq_encode_tr_kernel<false>;
+    auto kern = stats_sum ? tr::rvq_encode_tr_kernel<true, false>
+                          : (spec ? tr::rvq_encode_tr_kernel<false, true> : tr::rvq_encode_tr_kernel<false, false>);
     RVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(tr::NUM_THREADS, 1, 1);

@@ -3,8 +3,9 @@
 d <= 128 runs `rvq_encode_tr_kernel` (residual resident in tensor memory, norm term folded into the MMA, cluster
 multicast of the codebook stream); other d, or RVQ_KERNEL=tc, runs the generic `rvq_encode_tc_kernel`.  Both use the
 same exact fp32 scorer for every frame the fp16 filter cannot certify, so on the same input they must return
-bit-identical code indices and outputs, whatever the cluster size.  The environment switches are read once per
-process, hence the subprocesses.
+bit-identical code indices and outputs, whatever the cluster size - and whether the update waits for the exact
+re-rank or speculates on the approximate argmin and verifies / repairs afterwards (RVQ_SPEC=1).  The environment
+switches are read once per process, hence the subprocesses.
 """
 import os
 import subprocess
@@ -57,8 +58,8 @@ def run_variant(tmp_path, name, env, **kw):
 def test_tmem_resident_kernel_equals_generic_kernel(tmp_path, d, K, N, strided):
     kw = dict(nq=5, K=K, d=d, N=N, strided=strided, update=False)
     a = run_variant(tmp_path, "tr2", {"RVQ_CLUSTER": "2"}, **kw)
-    for name, env in [("tr1", {"RVQ_CLUSTER": "1"}), ("tr4", {"RVQ_CLUSTER": "4"}), ("tc", {"RVQ_KERNEL": "tc"}),
-                      ("tc2", {"RVQ_KERNEL": "tc", "RVQ_CLUSTER_TC": "2"})]:
+    for name, env in [("tr1", {"RVQ_CLUSTER": "1"}), ("tr4", {"RVQ_CLUSTER": "4"}), ("spec", {"RVQ_SPEC": "1"}),
+                      ("tc", {"RVQ_KERNEL": "tc"}), ("tc2", {"RVQ_KERNEL": "tc", "RVQ_CLUSTER_TC": "2"})]:
         b = run_variant(tmp_path, name, env, **kw)
         assert torch.equal(a["idx"], b["idx"]), name
         assert torch.equal(a["xq"], b["xq"]), name
