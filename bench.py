@@ -203,6 +203,14 @@ def main():
     n_warm = max(args.warmup, 40 if wl["update"] else 3)
     for _ in range(n_warm):
         step()
+    # ... and keep warming until the GPU has seen ~0.4 s of this kernel (a box fresh out of idle needs more than a
+    # handful of millisecond-long launches to reach its steady clocks); the timed region below is exactly K steps
+    torch.cuda.synchronize()
+    t_w = time.time()
+    while time.time() - t_w < 0.4:
+        step()
+        n_warm += 1
+        torch.cuda.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
