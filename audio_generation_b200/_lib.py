@@ -27,6 +27,9 @@ SIGNATURES = {
                         _vp, _sz, _i, _vp]),
     "rvq_ema_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "rvq_dequantize": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _i, _i, C.POINTER(_f), _i, _vp, _vp]),
+    "rvq_packed_bytes_per_frame": (_i, [_i, _i]),
+    "rvq_pack_indices": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
+    "rvq_unpack_indices": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
     "rvq_debug_stage_scores": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -350,6 +350,89 @@ extern "C" int rvq_dequantize(const float* cb, const long long* idx, long long N
     return RVQ_OK;
 }
 
+// ------------------------------------------------------------------------------------------ wire format
+// Codes of a frame packed LSB-first, `bits` bits per stage, frames byte-aligned: bytes_per_frame =
+// ceil(nq * bits / 8) (bits per frame of the codec = nq * log2 K, utils.py:137-147 bitrate_calculator).
+// One thread per frame; HBM-bound: reads 8 nq bytes, writes bytes_per_frame (pack) or the reverse (unpack).
+__global__ void pack_indices(const long long* __restrict__ idx, long long N, int nq, int bits, int bpf,
+                             uint8_t* __restrict__ out) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const long long* in = idx + n * nq;
+    uint8_t* o = out + n * bpf;
+    unsigned long long acc = 0;
+    int have = 0, w = 0;
+    const unsigned long long mask = (1ull << bits) - 1ull;
+    for (int q = 0; q < nq; ++q) {
+        acc |= ((unsigned long long)in[q] & mask) << have;
+        have += bits;
+        while (have >= 8) {
+            o[w++] = (uint8_t)(acc & 0xFFu);
+            acc >>= 8;
+            have -= 8;
+        }
+    }
+    if (have > 0) o[w] = (uint8_t)(acc & 0xFFu);
+}
+
+__global__ void unpack_indices(const uint8_t* __restrict__ in, long long N, int nq, int bits, int bpf,
+                               long long* __restrict__ idx) {
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint8_t* src = in + n * bpf;
+    long long* o = idx + n * nq;
+    unsigned long long acc = 0;
+    int have = 0, r = 0;
+    const unsigned long long mask = (1ull << bits) - 1ull;
+    for (int q = 0; q < nq; ++q) {
+        while (have < bits) {
+            acc |= (unsigned long long)src[r++] << have;
+            have += 8;
+        }
+        o[q] = (long long)(acc & mask);
+        acc >>= bits;
+        have -= bits;
+    }
+}
+
+static int check_wire(const char* who, long long N, int nq, int bits) {
+    if (N < 0 || nq <= 0 || bits < 1 || bits > 32) {
+        set_error("%s: bad argument (N=%lld nq=%d bits=%d; 1 <= bits <= 32)", who, N, nq, bits);
+        return RVQ_ERR_ARG;
+    }
+    return RVQ_OK;
+}
+
+extern "C" int rvq_packed_bytes_per_frame(int nq, int bits) { return (nq <= 0 || bits < 1 || bits > 32) ? RVQ_ERR_ARG : (nq * bits + 7) / 8; }
+
+extern "C" int rvq_pack_indices(const long long* idx, long long N, int nq, int bits, void* packed, void* stream) {
+    if (int e = check_wire("rvq_pack_indices", N, nq, bits)) return e;
+    if (N == 0) return RVQ_OK;
+    if (!idx || !packed) {
+        set_error("rvq_pack_indices: null pointer");
+        return RVQ_ERR_ARG;
+    }
+    const int block = 256;
+    pack_indices<<<(unsigned)((N + block - 1) / block), block, 0, static_cast<cudaStream_t>(stream)>>>(
+        idx, N, nq, bits, (nq * bits + 7) / 8, static_cast<uint8_t*>(packed));
+    RVQ_CUDA(cudaGetLastError());
+    return RVQ_OK;
+}
+
+extern "C" int rvq_unpack_indices(const void* packed, long long N, int nq, int bits, long long* idx, void* stream) {
+    if (int e = check_wire("rvq_unpack_indices", N, nq, bits)) return e;
+    if (N == 0) return RVQ_OK;
+    if (!idx || !packed) {
+        set_error("rvq_unpack_indices: null pointer");
+        return RVQ_ERR_ARG;
+    }
+    const int block = 256;
+    unpack_indices<<<(unsigned)((N + block - 1) / block), block, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(packed), N, nq, bits, (nq * bits + 7) / 8, idx);
+    RVQ_CUDA(cudaGetLastError());
+    return RVQ_OK;
+}
+
 // called from rvq_encode (rvq_abi.cu)
 int rvq_launch_exact_scan(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d,
                           int nq, int K, const float* cb, const float* meta, float* xq, long long* idx,

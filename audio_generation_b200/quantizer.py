@@ -299,6 +299,44 @@ class ResidualQuantizer(nn.Module):
                                               self.K, None, 0, _ptr(out), _stream()), "rvq_dequantize")
         return out.reshape(*idx.shape[:-1], self.dim)
 
+    # ------------------------------------------------------------------ wire format of the codes
+    @property
+    def code_bits(self) -> int:
+        """Bits per code on the wire: ceil(log2 K) (bits per frame = n * code_bits, utils.py:137-147)."""
+        return max(1, int(self.K - 1).bit_length())
+
+    def pack_indices(self, idx: torch.Tensor) -> torch.Tensor:
+        """idx (..., n) int64 -> uint8 (..., ceil(n * code_bits / 8)): codes of a frame LSB-first, byte-aligned frames."""
+        lib = _lib.load()
+        self._check_device(idx)
+        nq = idx.shape[-1]
+        flat = idx.reshape(-1, nq).contiguous().long()
+        N = flat.shape[0]
+        bpf = lib.rvq_packed_bytes_per_frame(nq, self.code_bits)
+        out = torch.empty((N, bpf), dtype=torch.uint8, device=idx.device)
+        with torch.cuda.device(idx.device):
+            _lib.check(lib.rvq_pack_indices(_ptr(flat), N, nq, self.code_bits, _ptr(out), _stream()), "rvq_pack_indices")
+        return out.reshape(*idx.shape[:-1], bpf)
+
+    def unpack_indices(self, packed: torch.Tensor, n: Optional[int] = None) -> torch.Tensor:
+        """Inverse of pack_indices: uint8 (..., bytes_per_frame) -> int64 (..., n)."""
+        lib = _lib.load()
+        self._check_device(packed)
+        nq = self.num_quantizers if n is None else int(n)
+        bpf = lib.rvq_packed_bytes_per_frame(nq, self.code_bits)
+        if packed.dtype != torch.uint8 or packed.shape[-1] != bpf:
+            raise ValueError(f"packed codes must be uint8 with {bpf} bytes per frame for n={nq}, K={self.K}")
+        flat = packed.reshape(-1, bpf).contiguous()
+        N = flat.shape[0]
+        out = torch.empty((N, nq), dtype=torch.int64, device=packed.device)
+        with torch.cuda.device(packed.device):
+            _lib.check(lib.rvq_unpack_indices(_ptr(flat), N, nq, self.code_bits, _ptr(out), _stream()), "rvq_unpack_indices")
+        return out.reshape(*packed.shape[:-1], nq)
+
+    def decode_packed(self, packed: torch.Tensor, n: Optional[int] = None) -> torch.Tensor:
+        """Wire bytes -> quantized latents (..., d): unpack + sum of code vectors (CausalVQAE.sample, vae.py:329-334)."""
+        return self.dequantize(self.unpack_indices(packed, n))
+
     # ------------------------------------------------------------------ epoch-level API
     def get_stale_clusters(self):
         """Per stage, the number of codes whose EMA usage share is below ``vq_cutoff_freq / K``."""

@@ -201,16 +201,21 @@ def main():
     # EMA workloads start from synthetic codebooks that the first updates pull towards the data (near-degenerate
     # codebooks, many exact re-ranks): time the steady state, not that transient
     n_warm = max(args.warmup, 40 if wl["update"] else 3)
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
     for _ in range(n_warm):
         step()
-    # ... and keep warming until the GPU has seen ~0.4 s of this kernel (a box fresh out of idle needs more than a
-    # handful of millisecond-long launches to reach its steady clocks); the timed region below is exactly K steps
+    w1.record()
     torch.cuda.synchronize()
-    t_w = time.time()
-    while time.time() - t_w < 0.4:
+    # ... and keep warming until the GPU has seen ~0.4 s of this kernel (a box fresh out of idle needs more than a
+    # handful of millisecond-long launches to reach its steady clocks).  The number of extra steps is agreed
+    # across ranks (EMA workloads all-reduce every step); the timed region below is exactly K steps.
+    extra = torch.tensor([max(0.0, 400.0 - w0.elapsed_time(w1)) / max(w0.elapsed_time(w1) / n_warm, 1e-3)], device=dev)
+    if world > 1:
+        dist.all_reduce(extra, op=dist.ReduceOp.MAX)
+    for _ in range(min(int(extra.item()), 2000)):
         step()
         n_warm += 1
-        torch.cuda.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

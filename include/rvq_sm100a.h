@@ -103,6 +103,15 @@ int rvq_dequantize(const float* cb, const long long* idx, long long N, long long
                    int d, int q0, int nq_use, int K, const float* w, int accumulate,
                    float* out, void* stream);
 
+/* Wire format of the codes (section 8f of SURVEY.md; bits per frame = nq * log2 K as in
+ * /root/reference/networks/utils.py:137-147 bitrate_calculator): the nq codes of a frame packed LSB-first,
+ * `bits` bits each (1..32), frames byte-aligned: rvq_packed_bytes_per_frame = ceil(nq * bits / 8).
+ *   idx    int64 [N, nq] (what rvq_encode writes / rvq_dequantize reads)
+ *   packed uint8 [N, bytes_per_frame]                                                          */
+int rvq_packed_bytes_per_frame(int nq, int bits); /* HOST; < 0 on bad arguments */
+int rvq_pack_indices(const long long* idx, long long N, int nq, int bits, void* packed, void* stream);
+int rvq_unpack_indices(const void* packed, long long N, int nq, int bits, long long* idx, void* stream);
+
 /* Bring-up / test hook: run ONE stage of the tensor-core filter for the first 128 frames of x
  * (contiguous [128, d]) and write the approximate scaled scores fp32 [128, Kpad] and the per-row
  * scale 2^a [128].  Not used by the product path. */

@@ -269,3 +269,32 @@ class ResidualQuantizerRef(nn.Module):
             self.vq_cutoff_freq = float(new_cutoff)
         if ratio is not None:
             self.vq_cutoff_freq *= float(ratio)
+
+
+# ----------------------------------------------------------------------------------------- wire format
+def pack_indices_ref(idx, bits):
+    """CPU restatement of the code wire format (include/rvq_sm100a.h: rvq_pack_indices): the n codes of a frame
+    LSB-first, `bits` bits each, frames byte-aligned.  bits per frame = n * log2 K as in the reference's
+    bitrate_calculator (/root/reference/networks/utils.py:137-147).  idx: int64 array-like [N, n] -> uint8 [N, ceil(n*bits/8)]."""
+    import numpy as np
+    a = np.asarray(idx, dtype=np.uint64)
+    N, n = a.shape
+    bpf = (n * bits + 7) // 8
+    out = np.zeros((N, bpf), dtype=np.uint8)
+    for f in range(N):
+        acc = 0
+        for q in range(n):
+            acc |= (int(a[f, q]) & ((1 << bits) - 1)) << (q * bits)
+        out[f] = np.frombuffer(acc.to_bytes(bpf, "little"), dtype=np.uint8)
+    return out
+
+
+def unpack_indices_ref(packed, n, bits):
+    import numpy as np
+    p_ = np.asarray(packed, dtype=np.uint8)
+    out = np.zeros((p_.shape[0], n), dtype=np.int64)
+    for f in range(p_.shape[0]):
+        acc = int.from_bytes(p_[f].tobytes(), "little")
+        for q in range(n):
+            out[f, q] = (acc >> (q * bits)) & ((1 << bits) - 1)
+    return out

@@ -317,3 +317,27 @@ def test_unsupported_shapes_are_refused():
         ResidualQuantizer(2, 100, "ema", 64).cuda()(torch.randn(8, 100, device="cuda"))       # d % 64 != 0
     with pytest.raises(RVQError):
         ResidualQuantizer(1, 64, "ema", 8448).cuda()(torch.randn(8, 64, device="cuda"))       # K > 8192
+
+
+@pytest.mark.parametrize("nq,K", [(8, 1024), (10, 512), (32, 4096), (5, 300), (3, 2)])
+def test_wire_format_matches_oracle_and_round_trips(nq, K):
+    """Packed codes: bit-exact against the oracle's packing, pack -> unpack is the identity, and
+    decode_packed(pack(idx)) equals the kernel's own xq."""
+    m = make(nq, K, 64)
+    m.eval()
+    x = torch.randn(3, 333, 64, device="cuda")
+    with torch.no_grad():
+        xq, idx, _ = m(x)
+        packed = m.pack_indices(idx)
+        back = m.unpack_indices(packed)
+        dec = m.decode_packed(packed)
+    bits = m.code_bits
+    assert packed.dtype == torch.uint8 and packed.shape == (3, 333, (nq * bits + 7) // 8)
+    ref = O.pack_indices_ref(idx.reshape(-1, nq).cpu().numpy(), bits)
+    assert (packed.reshape(-1, packed.shape[-1]).cpu().numpy() == ref).all()
+    assert torch.equal(back, idx)
+    assert (dec - xq).abs().max() <= 1e-5 * float(x.abs().max())
+    # partial stage count
+    with torch.no_grad():
+        p3 = m.pack_indices(idx[..., :min(3, nq)])
+        assert torch.equal(m.unpack_indices(p3, min(3, nq)), idx[..., :min(3, nq)])

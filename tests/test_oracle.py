@@ -115,3 +115,18 @@ def test_adjudicator_flags_real_errors():
     bad[5, 0] = (bad[5, 0] + 1) % 32
     a = O.adjudicate_indices(x, cbs, bad)
     assert a["n_mismatch"] >= 1 and a["n_illegal"] >= 1
+
+
+def test_wire_format_oracle_known_answer():
+    """Known answer of the LSB-first packing (10 bits per code, K = 1024) and the round trip."""
+    import numpy as np
+    from oracle import rvq_oracle as O
+    idx = np.array([[1, 2, 3], [1023, 0, 512]], dtype=np.int64)
+    packed = O.pack_indices_ref(idx, 10)
+    # frame 0: 1 | 2 << 10 | 3 << 20 = 0x300801 -> bytes 01 08 30 00 ; frame 1: 0x3FF | 512 << 20 = 0x200003FF
+    assert packed.tolist() == [[0x01, 0x08, 0x30, 0x00], [0xFF, 0x03, 0x00, 0x20]]
+    assert (O.unpack_indices_ref(packed, 3, 10) == idx).all()
+    rng = np.random.default_rng(0)
+    for bits, n in [(9, 10), (10, 8), (12, 32), (1, 5), (16, 3)]:
+        idx = rng.integers(0, 1 << bits, size=(50, n))
+        assert (O.unpack_indices_ref(O.pack_indices_ref(idx, bits), n, bits) == idx).all()
