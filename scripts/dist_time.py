@@ -15,17 +15,19 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 wl = bench.WORKLOADS["c3"]
-nq, K, d, N = wl["nq"], wl["K"], wl["d"], 1 << 19
+nq, K, d, N = wl["nq"], wl["K"], wl["d"], int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 19
+warm = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 m = ResidualQuantizer(nq, d, "ema", K)
 with torch.no_grad():
     m.codebooks.copy_(bench.synth_codebooks(nq, K, d))
     m.ema_sum.copy_(m.codebooks)
 m = m.to(dev).train()
-x = torch.randn(N, d, device=dev)
+g = torch.Generator(device=dev).manual_seed(1234 + rank)
+x = torch.randn(N, d, device=dev, generator=g)
 
 
-def timed(fn, reps=5):
-    for _ in range(2):
+def timed(fn, reps=5, warm_=2):
+    for _ in range(warm_):
         fn()
     torch.cuda.synchronize()
     if world > 1:
@@ -40,7 +42,7 @@ def timed(fn, reps=5):
 
 
 with torch.no_grad():
-    t_full = timed(lambda: m(x, None, update_codebook=True))
+    t_full = timed(lambda: m(x, None, update_codebook=True), reps=10, warm_=warm)
     m.eval()
     t_enc = timed(lambda: m(x, None))
     m.train()
@@ -48,6 +50,12 @@ with torch.no_grad():
     t_ar = timed(lambda: dist.all_reduce(flat)) if world > 1 else 0.0
     t_zero = timed(lambda: flat.zero_())
     t_prep = timed(lambda: (m.invalidate(), m._prepared()))
+t_all = torch.tensor([t_full, t_enc], device=dev)
+if world > 1:
+    gat = [torch.zeros_like(t_all) for _ in range(world)]
+    dist.all_gather(gat, t_all)
+    if rank == 0:
+        print("per-rank [step(update), encode-only] ms:", [[round(float(v), 2) for v in g_] for g_ in gat])
 if rank == 0:
     print(f"world={world} N/gpu={N}: step(update)={t_full:.3f} ms  encode-only={t_enc:.3f} ms  all_reduce({flat.numel()*4/1e6:.1f} MB)={t_ar:.3f} ms  "
           f"zero={t_zero:.3f} ms  prepare={t_prep:.3f} ms")
