@@ -217,13 +217,14 @@ def main():
         step()
         n_warm += 1
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.2)
+    time.sleep(0.2)              # every rank: a late rank 0 would make the others wait inside their timed region
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     ev0.record()
