@@ -30,6 +30,11 @@ SIGNATURES = {
     "rvq_packed_bytes_per_frame": (_i, [_i, _i]),
     "rvq_pack_indices": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
     "rvq_unpack_indices": (_i, [_vp, _ll, _i, _i, _vp, _vp]),
+    "rvq_som_spread": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), _i, _i, _i, _i, C.POINTER(_f), _vp]),
+    "rvq_reseed_frame": (C.c_ulonglong, [C.c_ulonglong, _i, _i, _i, C.c_ulonglong]),
+    "rvq_reseed_gather": (_i, [_vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _i, _vp, _vp, _vp, _f, _f, C.c_ulonglong, _ll, _ll,
+                               _vp, _vp]),
+    "rvq_reseed_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp]),
     "rvq_debug_stage_scores": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -25,6 +25,9 @@ from ._lib import RVQError, RVQ_ALGO_EXACT_SCAN, RVQ_ALGO_TENSOR
 
 EMA_DECAY = 0.99   # ASSUMED (rosinality / Jukebox lineage, README.md:26-27)
 EMA_EPS = 1e-5     # ASSUMED
+SOM_SHRINK = 0.1   # ASSUMED: SOM neighbourhood width 1 / (1 + SOM_SHRINK * update steps) (arXiv 2302.07950, README.md:10)
+SOM_MAX_RADIUS = 4
+_M64 = (1 << 64) - 1
 
 
 def tuple_checker(item, length):
@@ -41,6 +44,20 @@ def approximate_square_root(n: int):
     while h > 1 and n % h:
         h -= 1
     return h, n // h
+
+
+def som_weights(kernel_type: str, t: int, shrink: float = SOM_SHRINK):
+    """(radius, row-major weights) of the SOM neighbourhood after ``t`` updates: "hard" = the code itself 1 and its
+    four grid neighbours sigma_t = 1 / (1 + shrink t); "gaussian" = exp(-dist^2 / (2 sigma_t^2)) within
+    radius min(4, max(1, ceil(3 sigma_t)))."""
+    sigma = 1.0 / (1.0 + float(shrink) * float(t))
+    if kernel_type == "hard":
+        return 1, [0.0, sigma, 0.0, sigma, 1.0, sigma, 0.0, sigma, 0.0]
+    if kernel_type == "gaussian":
+        r = min(SOM_MAX_RADIUS, max(1, int(math.ceil(3.0 * sigma))))
+        return r, [math.exp(-(dy * dy + dx * dx) / (2.0 * sigma * sigma))
+                   for dy in range(-r, r + 1) for dx in range(-r, r + 1)]
+    raise ValueError(f"som_kernel_type must be 'hard' or 'gaussian', got {kernel_type!r}")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -147,7 +164,8 @@ class ResidualQuantizer(nn.Module):
 
     def __init__(self, num_quantizers, dim, quantizer_class="ema", codebook_sizes=1024,
                  vq_cutoff_freq=1, use_som=True, som_kernel_type="hard",
-                 decay=EMA_DECAY, eps=EMA_EPS, commitment_weight=1.0, algo="tensor"):
+                 decay=EMA_DECAY, eps=EMA_EPS, commitment_weight=1.0, algo="tensor",
+                 som_shrink=SOM_SHRINK, reseed_seed=0):
         super().__init__()
         if quantizer_class not in ("ema", "base"):
             raise ValueError(f"quantizer_class must be 'ema' or 'base', got {quantizer_class!r}")
@@ -158,6 +176,9 @@ class ResidualQuantizer(nn.Module):
         self.vq_cutoff_freq = float(vq_cutoff_freq)
         self.use_som = bool(use_som)
         self.som_kernel_type = som_kernel_type
+        if self.use_som:
+            som_weights(som_kernel_type, 0)        # validates the kernel type
+        self.som_shrink, self.reseed_seed = float(som_shrink), int(reseed_seed)
         self.decay, self.eps, self.commitment_weight = float(decay), float(eps), float(commitment_weight)
         self.algo = algo
         K = max(self.codebook_sizes)
@@ -170,16 +191,23 @@ class ResidualQuantizer(nn.Module):
         self.register_buffer("ema_count", torch.ones(self.num_quantizers, K))
         self.register_buffer("ema_sum", cb.detach().clone())
         self.register_buffer("k_valid", torch.tensor(self.codebook_sizes, dtype=torch.int32))
+        self.register_buffer("update_steps", torch.zeros((), dtype=torch.int64))   # EMA updates applied so far
+        self.register_buffer("n_replaced", torch.zeros(self.num_quantizers, dtype=torch.int32),
+                             persistent=False)                                     # codes re-seeded by the last update
+        self._steps_host = None    # host mirror of update_steps (read back once, then counted on the host)
+        self.register_load_state_dict_post_hook(lambda mod, _keys: setattr(mod, "_steps_host", None))
         self.quantizers = [_Stage(self, q) for q in range(self.num_quantizers)]
         self._derived = None       # (key, cb_op, cb_norm, cb_meta)
         self._ws = None
         self._stats = None
-        self.last_stats = None     # flat [sum | cnt] of the most recent update (kept for inspection)
+        self._spread = None
+        self.last_stats = None     # flat [sum | cnt | replacement vectors] of the most recent update (for inspection)
+        self.kernel_events = None  # a list collects (start, stop) CUDA events around every rvq_encode launch (bench.py)
 
     # ------------------------------------------------------------------ derived operands / scratch
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._derived = self._ws = self._stats = None
+        self._derived = self._ws = self._stats = self._spread = self._steps_host = None
         return out
 
     def _check_device(self, t: torch.Tensor):
@@ -219,11 +247,65 @@ class ResidualQuantizer(nn.Module):
         return self._ws
 
     def _stats_buffers(self, device):
+        """One flat fp32 buffer [nq K d sums | nq K counts | nq K d replacement vectors] = one all-reduce payload."""
         nq, K, d = self.num_quantizers, self.K, self.dim
         if self._stats is None or self._stats.device != device:
-            self._stats = torch.empty(nq * K * d + nq * K, dtype=torch.float32, device=device)
+            self._stats = torch.empty(2 * nq * K * d + nq * K, dtype=torch.float32, device=device)
+            self._spread = torch.empty(nq * K * d + nq * K, dtype=torch.float32, device=device)
         flat = self._stats
-        return flat, flat[: nq * K * d], flat[nq * K * d:]
+        return flat, flat[: nq * K * d], flat[nq * K * d: nq * K * (d + 1)], flat[nq * K * (d + 1):]
+
+    def _update_step_index(self) -> int:
+        if self._steps_host is None:
+            self._steps_host = int(self.update_steps)
+        return self._steps_host
+
+    def _update_codebooks(self, x3, N, L, sb, sl, sd, nq, idx, flat, ssum, scnt, rep):
+        """All-reduce of the statistics -> SOM neighbourhood -> EMA refresh -> stale-code re-seeding (K3 and
+        SURVEY 8f rows 2, 3), on the current stream."""
+        lib = _lib.load()
+        K, d = self.K, self.dim
+        cb = self.codebooks.detach()
+        dist = torch.distributed
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        t = self._update_step_index()
+        cutoff = self.vq_cutoff_freq
+        reseed = cutoff > 0
+        payload = flat
+        if reseed:
+            # replacement vectors need the codebooks `idx` was computed with: gathered BEFORE the EMA refresh; frames
+            # are numbered globally (equal shards per rank), non-owners contribute zeros to the sum
+            seed = (self.reseed_seed + t * 0xD1B54A32D192ED03) & _M64
+            _lib.check(lib.rvq_reseed_gather(_ptr(x3), N, L, sb, sl, sd, d, nq, K, _ptr(cb), _ptr(idx),
+                                             _ptr(self.ema_count), self.decay, cutoff, seed, rank * N, N * world,
+                                             _ptr(rep), _stream()), "rvq_reseed_gather")
+        else:
+            payload = flat[: self.num_quantizers * K * (d + 1)]
+        if world > 1:
+            # the only place the path crosses frame shards: one SUM all-reduce of [sum | cnt | rep]
+            dist.all_reduce(payload, op=dist.ReduceOp.SUM)
+        if self.use_som:
+            radius, w = som_weights(self.som_kernel_type, t, self.som_shrink)
+            hw = []
+            for q in range(nq):
+                hw += list(approximate_square_root(self.codebook_sizes[q]))
+            nsum = self.num_quantizers * K * d
+            ssum2, scnt2 = self._spread[:nsum], self._spread[nsum:]
+            _lib.check(lib.rvq_som_spread(_ptr(ssum), _ptr(scnt), _ptr(ssum2), _ptr(scnt2), (C.c_int * len(hw))(*hw),
+                                          nq, K, d, radius, (C.c_float * len(w))(*w), _stream()), "rvq_som_spread")
+            ssum, scnt = ssum2, scnt2
+        _lib.check(lib.rvq_ema_finalize(_ptr(cb), _ptr(self.ema_count), _ptr(self.ema_sum), _ptr(ssum), _ptr(scnt),
+                                        _ptr(self.k_valid), nq, K, d, self.decay, self.eps, _stream()),
+                   "rvq_ema_finalize")
+        if reseed:
+            _lib.check(lib.rvq_reseed_apply(_ptr(cb), _ptr(self.ema_count), _ptr(self.ema_sum), _ptr(rep),
+                                            _ptr(self.k_valid), nq, K, d, cutoff, cutoff, _ptr(self.n_replaced),
+                                            _stream()), "rvq_reseed_apply")
+        self.update_steps += 1
+        self._steps_host = t + 1
+        self._derived = None     # codebooks changed: operands are rebuilt before the next call
+        self.last_stats = flat
 
     # ------------------------------------------------------------------ the hot path
     def _encode(self, x: torch.Tensor, nq: int, update: bool, ws: Optional[torch.Tensor] = None):
@@ -242,25 +324,24 @@ class ResidualQuantizer(nn.Module):
         commit_sq = torch.empty(nq, dtype=torch.float64, device=dev)
         if ws is None:
             ws = self._workspace(dev)
-        ssum = scnt = flat = None
+        ssum = scnt = flat = rep = None
         if update:
-            flat, ssum, scnt = self._stats_buffers(dev)
-            flat.zero_()
+            flat, ssum, scnt, rep = self._stats_buffers(dev)
+            flat[: ssum.numel() + scnt.numel()].zero_()
         flags = RVQ_ALGO_EXACT_SCAN if self.algo == "exact_scan" else RVQ_ALGO_TENSOR
         with torch.cuda.device(dev):
+            if self.kernel_events is not None:
+                k0 = torch.cuda.Event(enable_timing=True)
+                k0.record()
             _lib.check(lib.rvq_encode(_ptr(x3), N, L, sb, sl, sd, self.dim, nq, self.K, _ptr(cb), _ptr(op), _ptr(nrm),
                                       _ptr(meta), _ptr(xq), _ptr(idx), _ptr(commit_sq), _ptr(ssum), _ptr(scnt),
                                       _ptr(ws), ws.numel(), flags, _stream()), "rvq_encode")
+            if self.kernel_events is not None:
+                k1 = torch.cuda.Event(enable_timing=True)
+                k1.record()
+                self.kernel_events.append((k0, k1))
             if update:
-                # the only place the path crosses frame shards: one SUM all-reduce of [sum | cnt]
-                if torch.distributed.is_available() and torch.distributed.is_initialized() \
-                        and torch.distributed.get_world_size() > 1:
-                    torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
-                _lib.check(lib.rvq_ema_finalize(_ptr(cb), _ptr(self.ema_count), _ptr(self.ema_sum), _ptr(ssum),
-                                                _ptr(scnt), _ptr(self.k_valid), nq, self.K, self.dim,
-                                                self.decay, self.eps, _stream()), "rvq_ema_finalize")
-                self._derived = None     # codebooks changed: operands are rebuilt before the next call
-                self.last_stats = flat
+                self._update_codebooks(x3, N, L, sb, sl, sd, nq, idx, flat, ssum, scnt, rep)
         xq = xq.reshape(x.shape) if xq.shape != x.shape else xq
         return xq, idx.reshape(*x.shape[:-1], nq), commit_sq
 
@@ -339,15 +420,11 @@ class ResidualQuantizer(nn.Module):
 
     # ------------------------------------------------------------------ epoch-level API
     def get_stale_clusters(self):
-        """Per stage, the number of codes whose EMA usage share is below ``vq_cutoff_freq / K``."""
-        cnt = self.ema_count
-        out = []
-        for q in range(self.num_quantizers):
-            K = self.codebook_sizes[q]
-            c = cnt[q, :K]
-            freq = c / c.sum().clamp_min(1e-30)
-            out.append(int((freq < self.vq_cutoff_freq / K).sum()))
-        return out
+        """Per stage, the number of codes whose EMA count (hits per call) is below ``vq_cutoff_freq`` - the codes the
+        next update re-seeds (``training.py:435,461``; threshold semantics ASSUMED: Jukebox / lucidrains lineage)."""
+        cnt = self.ema_count.cpu()
+        return [int((cnt[q, :self.codebook_sizes[q]] < self.vq_cutoff_freq).sum())
+                for q in range(self.num_quantizers)]
 
     def update_cutoff(self, new_cutoff=None, ratio=None):
         if new_cutoff is not None:

@@ -27,6 +27,9 @@ WORKLOADS = {
                desc="BASELINE configs[1]: RVQ encode only, 8 quantizers x 1024 codes, d=128, 1M synthetic frames"),
     "c3": dict(nq=12, K=1024, d=256, frames=1 << 20, update=True,
                desc="BASELINE configs[2]: RVQ encode + EMA update, 12 x 1024 codes, d=256, 1M frames per GPU"),
+    "c3m": dict(nq=12, K=1024, d=256, frames=1 << 20, update=True, som=True, cutoff=1.0,
+                desc="c3 plus codebook maintenance (SURVEY 8f rows 2-3): SOM neighbourhood spreading (hard kernel) and "
+                     "stale-code re-seeding (vq_cutoff_freq=1) every step"),
     "c4s": dict(nq=32, K=4096, d=512, frames=1 << 17, update=False,
                 desc="BASELINE configs[3] shape (32 x 4096 codes, d=512), 128K frames per GPU"),
     "c5q": dict(nq=8, K=1024, d=512, frames=1 << 18, update=False,
@@ -185,7 +188,10 @@ def main():
     peaks = load_peaks()
     nq, K, d, N = wl["nq"], wl["K"], wl["d"], wl["frames"]
 
-    quant = ResidualQuantizer(nq, d, "ema", K, algo=args.algo)
+    # c2/c3 time the north-star path (encode [+ EMA count/sum, all-reduce, refresh]); the SOM neighbourhood and
+    # stale-code re-seeding of SURVEY 8f are switched on by the c3m workload only
+    quant = ResidualQuantizer(nq, d, "ema", K, algo=args.algo, use_som=bool(wl.get("som", False)),
+                              vq_cutoff_freq=float(wl.get("cutoff", 0.0)))
     with torch.no_grad():
         quant.codebooks.copy_(synth_codebooks(nq, K, d))
         quant.ema_sum.copy_(quant.codebooks)
@@ -226,6 +232,7 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    quant.kernel_events = []          # (start, stop) CUDA events around every rvq_encode launch, on the launch stream
     t_wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
@@ -234,6 +241,8 @@ def main():
     torch.cuda.synchronize()
     t_wall1 = time.time()
     ms = ev0.elapsed_time(ev1)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.kernel_events)
+    quant.kernel_events = None
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -246,6 +255,39 @@ def main():
 
     # ---- e2e: host pinned frames -> codes on the host, through the public HostEncoder API
     e2e = None
+    if not args.no_e2e and wl["update"]:
+        # training-side call: pinned host latents -> device, forward with codebook update, commit loss back to the host
+        n_e2e = min(N, 1 << 19)
+        xh = torch.randn(n_e2e, d).pin_memory()
+        xd = torch.empty(n_e2e, d, device=dev)
+        loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            xd.copy_(xh, non_blocking=True)
+            with torch.no_grad():
+                _, _, commit = quant(xd, None, update_codebook=True)
+            loss_h.copy_(commit, non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(reps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ems], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = dict(value=n_e2e * world * reps / (ems * 1e-3), unit="frames/s", h2d_bytes_per_step=n_e2e * d * 4,
+                   d2h_bytes_per_step=4, frames_per_step=n_e2e,
+                   api="som_quantizer.ResidualQuantizer.forward(update_codebook=True) on host-fed latents")
     if not args.no_e2e and not wl["update"]:
         n_e2e = min(N, 1 << 19)
         xh = torch.randn(n_e2e, d).pin_memory()
@@ -280,7 +322,7 @@ def main():
 
     flops_per_frame = nq * 2 * K * d
     per_gpu_rate = value / world
-    achieved = per_gpu_rate * flops_per_frame / 1e12
+    achieved = N * flops_per_frame / (kernel_ms * 1e-3) / 1e12      # the fused encode kernel alone (rank 0)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -292,7 +334,10 @@ def main():
                     traffic=traffic, peak_source=peaks["source"] + " (burst bf16 cuBLAS 8192^3)",
                     frac_of_sustained=achieved / peaks["bf16_sustained"], frac_of_spec=achieved / SPEC_BF16_TFLOPS,
                     kernel="rvq_encode_tr_kernel" if d <= 128 else "rvq_encode_tc_kernel", flops_per_frame=flops_per_frame,
-                    note="algorithmic flops = nq*2*K*d per frame (distance GEMM only)")
+                    kernel_ms=kernel_ms, step_frac_of_peak=per_gpu_rate * flops_per_frame / 1e12 / peaks["bf16"],
+                    note="algorithmic flops = nq*2*K*d per frame (distance GEMM only); achieved = frames per launch x "
+                         "flops per frame / mean launch duration of the fused encode kernel (CUDA events on the launch "
+                         "stream inside the timed region); step_frac_of_peak uses the whole step instead")
     cpu = None
     if not args.no_cpu and world == 1:
         threads = os.cpu_count() or 1
@@ -302,13 +347,16 @@ def main():
         cpu = dict(value=rate, unit="frames/s", cores=threads, kind="port",
                    sample=f"{sample} frames of the same workload in {dt:.2f}s; oracle/rvq_oracle.py restatement "
                           f"(upstream som_quantizer not installable)")
+    # kernels of librvq_sm100a.so per step: the fused encode; with the update also k3_counts + k3_codes (EMA refresh)
+    # and k0_stage_max + k0_convert (operands of the refreshed codebooks); c3m adds som_spread, reseed_gather/apply
+    launches_per_step = 1 + (4 if wl["update"] else 0) + (1 if wl.get("som") else 0) + (2 if wl.get("cutoff") else 0)
     out = dict(metric="rvq_frames_per_sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
                warmup=n_warm, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
                vs_baseline=None, dtype="f16-filter/f32-exact", data="synthetic",
                config=dict(workload=args.workload, desc=wl["desc"], nq=nq, K=K, d=d, frames_per_gpu=N,
                            update_codebook=wl["update"], parallelism=f"frames sharded x{world}, codebooks replicated",
                            l2="inputs (%.0f MB) larger than L2; no explicit flush" % (N * d * 4 / 1e6), algo=args.algo),
-               roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=args.steps * (3 if wl["update"] else 1),
+               roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=args.steps * launches_per_step,
                clocks=clocks)
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RVQ_ABI_VERSION 4
+#define RVQ_ABI_VERSION 5
 
 typedef enum {
     RVQ_OK = 0,
@@ -111,6 +111,38 @@ int rvq_dequantize(const float* cb, const long long* idx, long long N, long long
 int rvq_packed_bytes_per_frame(int nq, int bits); /* HOST; < 0 on bad arguments */
 int rvq_pack_indices(const long long* idx, long long N, int nq, int bits, void* packed, void* stream);
 int rvq_unpack_indices(const void* packed, long long N, int nq, int bits, long long* idx, void* stream);
+
+/* Self-organising-map neighbourhood of the EMA statistics (use_som / som_kernel_type of the reference's
+ * constructor, /root/reference/networks/vae.py:220-221,250-251; the map of stage q is a height x width grid with
+ * height * width = number of codes, /root/reference/networks/utils.py:244-245,257).  Runs after the cross-GPU
+ * all-reduce and before rvq_ema_finalize:
+ *   out[q, (y, x)] = sum_{dy, dx in [-radius, radius]} weights[dy + radius][dx + radius] * in[q, (y + dy, x + dx)]
+ * neighbours outside the grid are skipped (no wrap-around), codes beyond height * width pass through.  The terms
+ * are added in row-major (dy, dx) order with separate fp32 multiply and add; zero weights are skipped.
+ *   grid_hw HOST int[2 * nq_use] = {height, width} per stage;  weights HOST float[(2 radius + 1)^2];
+ *   radius <= 4, nq_use <= 64;  out_* must not alias stats_*.                                           */
+int rvq_som_spread(const float* stats_sum, const float* stats_cnt, float* out_sum, float* out_cnt,
+                   const int* grid_hw, int nq_use, int K, int d, int radius, const float* weights, void* stream);
+
+/* Stale-code re-seeding (vq_cutoff_freq of the reference's constructor, vae.py:213,249; get_stale_clusters /
+ * update_cutoff, /root/reference/networks/training.py:435,454,461).
+ * rvq_reseed_frame (HOST, pure): the global frame whose stage-q residual re-seeds code (q, k):
+ *   z = seed + (q K + k + 1) * 0x9E3779B97F4A7C15;  z = (z ^ z >> 30) * 0xBF58476D1CE4E5B9;
+ *   z = (z ^ z >> 27) * 0x94D049BB133111EB;  z ^= z >> 31;  frame = z mod frames_total       (64-bit wrap-around)
+ * rvq_reseed_gather: rep[q, k, :] = x[n] - sum_{s < q} cb[s, idx[n, s], :] (fp32, stage order: the residual the
+ *   encode kernel saw) for n = frame - frame_offset when 0 <= n < N, zeros otherwise - so that a SUM all-reduce of
+ *   rep over ranks holding disjoint frame ranges leaves the owner's vector on every replica.  Must run BEFORE
+ *   rvq_ema_finalize (it needs the codebooks idx was computed with).  ema_count (nullable): codes with
+ *   decay * ema_count >= cutoff cannot become stale in this step and get zeros without touching x.
+ * rvq_reseed_apply (after rvq_ema_finalize): every valid code with ema_count < cutoff takes cb = rep,
+ *   ema_sum = rep * reset_count, ema_count = reset_count;  n_replaced DEVICE int[nq_use] (nullable) = how many.  */
+unsigned long long rvq_reseed_frame(unsigned long long seed, int q, int K, int k, unsigned long long frames_total);
+int rvq_reseed_gather(const float* x, long long N, long long L, long long stride_b, long long stride_l,
+                      long long stride_d, int d, int nq_use, int K, const float* cb, const long long* idx,
+                      const float* ema_count, float decay, float cutoff, unsigned long long seed,
+                      long long frame_offset, long long frames_total, float* rep, void* stream);
+int rvq_reseed_apply(float* cb, float* ema_count, float* ema_sum, const float* rep, const int* k_valid,
+                     int nq_use, int K, int d, float cutoff, float reset_count, int* n_replaced, void* stream);
 
 /* Bring-up / test hook: run ONE stage of the tensor-core filter for the first 128 frames of x
  * (contiguous [128, d]) and write the approximate scaled scores fp32 [128, Kpad] and the per-row

@@ -165,6 +165,106 @@ def adjudicate_indices(x2d, codebooks, idx_test: torch.Tensor, eps_scale: float 
 
 
 # --------------------------------------------------------------------------
+# codebook maintenance around the EMA update -- every choice ASSUMED
+# --------------------------------------------------------------------------
+SOM_SHRINK = 0.1      # ASSUMED: neighbourhood width sigma_t = 1 / (1 + SOM_SHRINK * t), t = update steps so far
+SOM_MAX_RADIUS = 4
+
+
+def som_weights(kernel_type: str, t: int, shrink: float = SOM_SHRINK):
+    """(radius, float32 weights [(2r+1), (2r+1)]) of the SOM neighbourhood at update step ``t``.
+
+    Restates the neighbourhood functions of Irie et al., "Self-organising neural discrete representation
+    learning a la Kohonen" (arXiv 2302.07950, the SOM paper ``/root/reference/README.md:10`` cites), with the
+    time-shrinking width sigma_t = 1 / (1 + shrink * t):
+      "hard"      the code itself 1, its four grid neighbours (Manhattan distance 1) sigma_t, everything else 0;
+      "gaussian"  exp(-(dy^2 + dx^2) / (2 sigma_t^2)) inside the window of radius min(4, max(1, ceil(3 sigma_t))).
+    """
+    import numpy as np
+    sigma = 1.0 / (1.0 + float(shrink) * float(t))
+    if kernel_type == "hard":
+        w = np.zeros((3, 3), dtype=np.float32)
+        w[1, 1] = 1.0
+        w[0, 1] = w[2, 1] = w[1, 0] = w[1, 2] = np.float32(sigma)
+        return 1, w
+    if kernel_type == "gaussian":
+        r = min(SOM_MAX_RADIUS, max(1, int(math.ceil(3.0 * sigma))))
+        w = np.zeros((2 * r + 1, 2 * r + 1), dtype=np.float32)
+        for dy in range(-r, r + 1):
+            for dx in range(-r, r + 1):
+                w[dy + r, dx + r] = np.float32(math.exp(-(dy * dy + dx * dx) / (2.0 * sigma * sigma)))
+        return r, w
+    raise ValueError(f"som_kernel_type must be 'hard' or 'gaussian', got {kernel_type!r}")
+
+
+def som_spread_ref(sm, cnt, height: int, width: int, radius: int, weights):
+    """Neighbourhood spreading of one stage's statistics on its ``height x width`` map (row-major codes):
+    out[(y, x)] = sum_{dy, dx} w[dy, dx] * in[(y + dy, x + dx)], neighbours outside the grid skipped, zero weights
+    skipped, terms added in row-major (dy, dx) order with separate float32 multiply and add.  Codes beyond
+    height * width pass through.  ``sm`` (K, d), ``cnt`` (K,) -> float32 numpy arrays of the same shapes."""
+    import numpy as np
+    sm = np.asarray(sm, dtype=np.float32)
+    cnt = np.asarray(cnt, dtype=np.float32)
+    K, d = sm.shape
+    n = height * width
+    full = np.concatenate([sm, cnt[:, None]], axis=1)
+    grid = full[:n].reshape(height, width, d + 1)
+    acc = np.zeros_like(grid)
+    for dy in range(-radius, radius + 1):
+        for dx in range(-radius, radius + 1):
+            w = np.float32(weights[dy + radius][dx + radius])
+            if w == 0:
+                continue
+            y0, y1 = max(0, -dy), min(height, height - dy)
+            x0, x1 = max(0, -dx), min(width, width - dx)
+            if y0 >= y1 or x0 >= x1:
+                continue
+            acc[y0:y1, x0:x1] = acc[y0:y1, x0:x1] + w * grid[y0 + dy:y1 + dy, x0 + dx:x1 + dx]
+    out = full.copy()
+    out[:n] = acc.reshape(n, d + 1)
+    return out[:, :d].copy(), out[:, d].copy()
+
+
+_M64 = (1 << 64) - 1
+
+
+def reseed_frame_ref(seed: int, q: int, K: int, k: int, frames_total: int) -> int:
+    """Global frame whose stage-q residual re-seeds code (q, k): splitmix64 finaliser of
+    ``seed + (q K + k + 1) * 0x9E3779B97F4A7C15`` (64-bit wrap-around), modulo ``frames_total``."""
+    z = (seed + (q * K + k + 1) * 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    z ^= z >> 31
+    return z % frames_total
+
+
+def reseed_vectors_ref(r_q, q: int, K: int, seed: int, frame_offset: int = 0, frames_total: Optional[int] = None):
+    """Replacement vector of every code of stage ``q``: the stage-q residual ``r_q[n]`` of the frame
+    ``n = reseed_frame_ref(seed, q, K, k, frames_total) - frame_offset``, zeros when another rank owns that frame
+    (the caller sums over ranks).  (K, d) float32."""
+    N, d = r_q.shape
+    total = N if frames_total is None else int(frames_total)
+    rep = torch.zeros(K, d, dtype=torch.float32)
+    for k in range(K):
+        n = reseed_frame_ref(seed, q, K, k, total) - frame_offset
+        if 0 <= n < N:
+            rep[k] = r_q[n].float()
+    return rep
+
+
+def reseed_apply_ref(cb, ema_count, ema_sum, rep, cutoff: float, reset_count: float):
+    """Dead-code re-seeding of one stage after its EMA refresh (lineage: Jukebox ``restore_k`` / lucidrains
+    ``expire_codes_``; ASSUMED): every code with ``ema_count < cutoff`` takes ``rep[k]``,
+    ``ema_sum = rep[k] * reset_count``, ``ema_count = reset_count``.  Returns (cb, ema_count, ema_sum, n_replaced)."""
+    stale = ema_count < cutoff
+    rc = torch.tensor(reset_count, dtype=torch.float32)
+    cb = torch.where(stale[:, None], rep, cb)
+    ema_sum = torch.where(stale[:, None], rep * rc, ema_sum)
+    ema_count = torch.where(stale, rc, ema_count)
+    return cb, ema_count, ema_sum, int(stale.sum())
+
+
+# --------------------------------------------------------------------------
 # nn.Module with the reference's call-site contract (SURVEY Appendix A)
 # --------------------------------------------------------------------------
 class _SOMGrid:
@@ -193,8 +293,9 @@ class ResidualQuantizerRef(nn.Module):
 
     def __init__(self, num_quantizers, dim, quantizer_class="ema", codebook_sizes=1024,
                  vq_cutoff_freq=1, use_som=True, som_kernel_type="hard",
-                 decay=EMA_DECAY, eps=EMA_EPS, commitment_weight=1.0):
+                 decay=EMA_DECAY, eps=EMA_EPS, commitment_weight=1.0, som_shrink=SOM_SHRINK, reseed_seed=0):
         super().__init__()
+        self.som_shrink, self.reseed_seed = float(som_shrink), int(reseed_seed)
         self.num_quantizers = int(num_quantizers)
         self.dim = int(dim)
         self.quantizer_class = quantizer_class
@@ -211,7 +312,12 @@ class ResidualQuantizerRef(nn.Module):
             self.register_buffer("codebooks", cb)
         self.register_buffer("ema_count", torch.ones(self.num_quantizers, Kmax))
         self.register_buffer("ema_sum", cb.detach().clone())
+        self.register_buffer("update_steps", torch.zeros((), dtype=torch.int64))
         self.quantizers = [_StageRef(self, q) for q in range(self.num_quantizers)]
+        self.n_replaced = [0] * self.num_quantizers          # codes re-seeded by the last update
+
+    def step_seed(self):
+        return (self.reseed_seed + int(self.update_steps) * 0xD1B54A32D192ED03) & _M64
 
     def forward(self, x, n=None, update_codebook=False, prioritize_early=False):
         if prioritize_early:
@@ -235,11 +341,29 @@ class ResidualQuantizerRef(nn.Module):
             if update_codebook and self.training and self.quantizer_class == "ema":
                 with torch.no_grad():
                     cnt, sm = ema_stats_ref(r.detach(), i, K)
-                    if torch.distributed.is_available() and torch.distributed.is_initialized():
+                    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+                    rank = torch.distributed.get_rank() if dist_on else 0
+                    world = torch.distributed.get_world_size() if dist_on else 1
+                    rep = None
+                    if self.vq_cutoff_freq > 0:        # replacement vectors for stale codes (equal shards ASSUMED)
+                        rep = reseed_vectors_ref(r.detach(), q, max(self.codebook_sizes), self.step_seed(),
+                                                 rank * N, N * world)[:K]
+                    if dist_on:
                         torch.distributed.all_reduce(cnt)
                         torch.distributed.all_reduce(sm)
+                        if rep is not None:
+                            torch.distributed.all_reduce(rep)
+                    if self.use_som:                   # SOM neighbourhood of the (all-reduced) statistics
+                        radius, w = som_weights(self.som_kernel_type, int(self.update_steps), self.som_shrink)
+                        h, wd = approximate_square_root(K)
+                        sm_, cnt_ = som_spread_ref(sm.numpy(), cnt.numpy(), h, wd, radius, w)
+                        sm, cnt = torch.from_numpy(sm_), torch.from_numpy(cnt_)
                     ncb, nc, ns = ema_finalize_ref(cb, self.ema_count[q, :K], self.ema_sum[q, :K], cnt, sm,
                                                    self.decay, self.eps)
+                    if rep is not None:
+                        ncb, nc, ns, nrep = reseed_apply_ref(ncb, nc, ns, rep, self.vq_cutoff_freq,
+                                                             self.vq_cutoff_freq)
+                        self.n_replaced[q] = nrep
                     self._pending = getattr(self, "_pending", [])
                     self._pending.append((q, K, ncb, nc, ns))
             xq = xq + z.detach()
@@ -249,6 +373,8 @@ class ResidualQuantizerRef(nn.Module):
             self.codebooks.data[q, :K] = ncb
             self.ema_count[q, :K] = nc
             self.ema_sum[q, :K] = ns
+        if getattr(self, "_pending", []):
+            self.update_steps += 1
         self._pending = []
         xf = x.reshape(-1, self.dim)
         x_quantized = (xf + (xq - xf).detach()).reshape(shp)           # straight-through
@@ -256,13 +382,10 @@ class ResidualQuantizerRef(nn.Module):
         return x_quantized, index, commit
 
     def get_stale_clusters(self):
-        out = []
-        for q in range(self.num_quantizers):
-            K = self.codebook_sizes[q]
-            c = self.ema_count[q, :K]
-            freq = c / c.sum().clamp_min(1e-30)
-            out.append(int((freq < self.vq_cutoff_freq / K).sum()))
-        return out
+        """Per stage, the number of codes whose EMA count (hits per call) is below ``vq_cutoff_freq`` (ASSUMED:
+        the dead-code threshold of the Jukebox / lucidrains lineage, in count units)."""
+        return [int((self.ema_count[q, :self.codebook_sizes[q]] < self.vq_cutoff_freq).sum())
+                for q in range(self.num_quantizers)]
 
     def update_cutoff(self, new_cutoff=None, ratio=None):
         if new_cutoff is not None:

@@ -166,9 +166,12 @@ def test_ragged_codebook_sizes():
 
 @pytest.mark.parametrize("algo", ["tensor", "exact_scan"])
 def test_ema_update_matches_oracle(algo):
+    """The north-star update (counts + summed vectors -> EMA refresh), SOM spreading and re-seeding switched off;
+    tests/test_gpu_codebook_maintenance.py covers them."""
     nq, K, d, N = 3, 512, 128, 20000
     m = make(nq, K, d, algo=algo)
-    ref = O.ResidualQuantizerRef(nq, d, "ema", K)
+    m.use_som, m.vq_cutoff_freq = False, 0.0
+    ref = O.ResidualQuantizerRef(nq, d, "ema", K, use_som=False, vq_cutoff_freq=0)
     with torch.no_grad():
         ref.codebooks.copy_(m.codebooks.cpu())
         ref.ema_sum.copy_(m.ema_sum.cpu())
@@ -189,7 +192,7 @@ def test_ema_update_matches_oracle(algo):
         assert torch.allclose(m.codebooks.cpu(), ref.codebooks.detach(), rtol=1e-4, atol=1e-4)
     # statistics identity: counts sum to N per stage
     flat = m.last_stats
-    cnts = flat[nq * K * d:].reshape(nq, K)
+    cnts = flat[nq * K * d: nq * K * (d + 1)].reshape(nq, K)
     assert torch.allclose(cnts.sum(1).cpu(), torch.full((nq,), float(N)))
 
 

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.rvq_version() == 4
+    assert lib.rvq_version() == 5
 
 
 def test_argument_checks_need_no_gpu():
@@ -49,7 +49,7 @@ def test_module_is_a_drop_in_on_the_host_side():
     e = ResidualQuantizer(8, 512, "ema", 1024)
     assert list(e.parameters()) == []                                                    # training.py:516 may be empty
     sd = e.state_dict()
-    assert set(sd) == {"codebooks", "ema_count", "ema_sum", "k_valid"}                   # derived operands not persisted
+    assert set(sd) == {"codebooks", "ema_count", "ema_sum", "k_valid", "update_steps"}                 # derived operands not persisted
     e2 = ResidualQuantizer(8, 512, "ema", 1024)
     e2.load_state_dict(sd)
     assert torch.equal(e2.codebooks, e.codebooks)

@@ -130,3 +130,62 @@ def test_wire_format_oracle_known_answer():
     for bits, n in [(9, 10), (10, 8), (12, 32), (1, 5), (16, 3)]:
         idx = rng.integers(0, 1 << bits, size=(50, n))
         assert (O.unpack_indices_ref(O.pack_indices_ref(idx, bits), n, bits) == idx).all()
+
+
+def test_som_spread_oracle_known_answer():
+    """Hand-computed 2 x 3 map, hard neighbourhood with sigma = 0.5: every cell = itself + 0.5 * its 4-neighbours."""
+    import numpy as np
+    radius, w = O.som_weights("hard", t=10, shrink=0.1)          # sigma = 1 / (1 + 1) = 0.5
+    assert radius == 1 and w.tolist() == [[0, 0.5, 0], [0.5, 1, 0.5], [0, 0.5, 0]]
+    cnt = np.array([1, 2, 4, 8, 16, 32, 99, 77], dtype=np.float32)       # K = 8: two padding codes beyond the map
+    sm = np.stack([cnt, -cnt], axis=1)
+    osm, ocnt = O.som_spread_ref(sm, cnt, 2, 3, radius, w)
+    # grid [[1, 2, 4], [8, 16, 32]]
+    assert ocnt.tolist() == [1 + 0.5 * (2 + 8), 2 + 0.5 * (1 + 4 + 16), 4 + 0.5 * (2 + 32),
+                             8 + 0.5 * (1 + 16), 16 + 0.5 * (2 + 8 + 32), 32 + 0.5 * (4 + 16), 99, 77]
+    assert (osm[:, 0] == ocnt).all() and (osm[:, 1] == -ocnt).all()
+    # step 0: sigma = 1 -> plain 5-point sum; gaussian weights are symmetric and peak at the centre
+    assert O.som_weights("hard", 0)[1][0, 1] == 1.0
+    r, g = O.som_weights("gaussian", 0)
+    assert r == 3 and g[3, 3] == 1.0 and (g == g.T).all() and (g == g[::-1, ::-1]).all()
+    assert abs(float(g[3, 4]) - 0.60653066) < 1e-7
+    with pytest.raises(ValueError):
+        O.som_weights("soft", 0)
+
+
+def test_reseed_oracle_matches_library_hash_and_known_answer():
+    """The frame choice of the stale-code re-seeding is a stated contract (include/rvq_sm100a.h): the oracle's
+    Python restatement, the library's host function and a hand-evaluated splitmix64 value must agree."""
+    from audio_generation_b200 import _lib
+    lib = _lib.load()
+    # splitmix64 finaliser of 0x9E3779B97F4A7C15 (seed 0, q = k = 0) is the first output of SplitMix64(0)
+    assert O.reseed_frame_ref(0, 0, 1024, 0, 1 << 64) == 0xE220A8397B1DCDAF
+    for seed, q, K, k, total in [(0, 0, 1024, 0, 1 << 20), (123456789, 3, 512, 17, 600), (2 ** 64 - 1, 11, 1024, 1023, 7),
+                                 (0xD1B54A32D192ED03, 5, 4096, 4095, 1 << 24)]:
+        assert lib.rvq_reseed_frame(seed, q, K, k, total) == O.reseed_frame_ref(seed, q, K, k, total)
+    cb = torch.arange(8.0).reshape(4, 2)
+    cnt = torch.tensor([5.0, 0.2, 1.0, 0.99])
+    rep = torch.full((4, 2), -1.0)
+    ncb, nc, ns, n = O.reseed_apply_ref(cb, cnt, cb * 2, rep, cutoff=1.0, reset_count=1.0)
+    assert n == 2 and nc.tolist() == [5.0, 1.0, 1.0, 1.0]
+    assert ncb.tolist() == [[0, 1], [-1, -1], [4, 5], [-1, -1]] and ns[1].tolist() == [-1, -1] and ns[0].tolist() == [0, 2]
+
+
+def test_module_update_with_som_and_reseed_cpu():
+    """Ref module: a never-selected code goes stale and is replaced by a residual of the batch; replicas of the
+    update (same seed) agree bit for bit; the SOM spread leaves the total count unchanged only for sigma -> 0."""
+    torch.manual_seed(3)
+    m = O.ResidualQuantizerRef(2, 8, "ema", 16, vq_cutoff_freq=1.0, use_som=True).train()
+    with torch.no_grad():
+        m.codebooks[0, 5] = 1e3                                   # far away: never selected
+        m.ema_sum.copy_(m.codebooks)
+        m.ema_count[0, 5] = 0.5
+    x = torch.randn(64, 8)
+    assert m.get_stale_clusters() == [1, 0]
+    with torch.no_grad():
+        m(x, None, update_codebook=True)
+    assert int(m.update_steps) == 1
+    # code (0, 5): count 0.5 * 0.99 + spread of its neighbours' hits; re-seeded only if still below the cutoff
+    n = O.reseed_frame_ref(m.reseed_seed, 0, 16, 5, 64)
+    assert float(m.ema_count[0, 5]) == 1.0 and torch.equal(m.codebooks[0, 5], x[n])      # stage 0 residual = x
+    assert torch.equal(m.ema_sum[0, 5], x[n])
