@@ -35,6 +35,7 @@ SIGNATURES = {
     "rvq_reseed_gather": (_i, [_vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _i, _vp, _vp, _vp, _f, _f, C.c_ulonglong, _ll, _ll,
                                _vp, _vp]),
     "rvq_reseed_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp]),
+    "rvq_backward": (_i, [_vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp]),
     "rvq_debug_stage_scores": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

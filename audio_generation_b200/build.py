@@ -11,7 +11,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = Path(__file__).resolve().parent / "librvq_sm100a.so"
-SOURCES = ["rvq_abi.cu", "rvq_aux.cu", "rvq_encode_tc.cu", "rvq_encode_tr.cu", "rvq_codebook.cu"]
+SOURCES = ["rvq_abi.cu", "rvq_aux.cu", "rvq_encode_tc.cu", "rvq_encode_tr.cu", "rvq_codebook.cu", "rvq_backward.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "exact.cuh", "encode_common.cuh", "../../include/rvq_sm100a.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -135,27 +135,11 @@ class _RVQFunction(torch.autograd.Function):
     def backward(ctx, g_out, _g_idx, g_commit):
         x, idx, codebooks = ctx.saved_tensors
         mod, nq = ctx.mod, ctx.nq
-        d = mod.dim
-        gx = g_out if ctx.needs_input_grad[0] else None
-        gcb = None
+        need_x = ctx.needs_input_grad[0]
         need_cb = ctx.needs_input_grad[1] and mod.quantizer_class == "base"
-        if g_commit is not None and (ctx.needs_input_grad[0] or need_cb):
-            xf = x.reshape(-1, d)
-            flat = idx.reshape(-1, nq)
-            N = flat.shape[0]
-            coef = g_commit * (2.0 / (N * d))
-            r = xf
-            acc = torch.zeros_like(xf)
-            if need_cb:
-                gcb = torch.zeros_like(codebooks)
-            for q in range(nq):
-                r = r - codebooks[q].detach()[flat[:, q]]
-                acc = acc + r
-                if need_cb:
-                    gcb[q].index_add_(0, flat[:, q], r * (-coef))
-            if ctx.needs_input_grad[0]:
-                gxc = (acc * (coef * mod.commitment_weight)).reshape(x.shape)
-                gx = gxc if gx is None else gx + gxc
+        if g_commit is None or not (need_x or need_cb):
+            return (g_out if need_x else None), None, None, None, None
+        gx, gcb = mod._backward(x, idx, codebooks.detach(), nq, g_out if need_x else None, g_commit, need_x, need_cb)
         return gx, gcb, None, None, None
 
 
@@ -344,6 +328,34 @@ class ResidualQuantizer(nn.Module):
                 self._update_codebooks(x3, N, L, sb, sl, sd, nq, idx, flat, ssum, scnt, rep)
         xq = xq.reshape(x.shape) if xq.shape != x.shape else xq
         return xq, idx.reshape(*x.shape[:-1], nq), commit_sq
+
+    def _backward(self, x, idx, cb, nq, g_out, g_commit, need_x, need_cb):
+        """rvq_backward: gx = g_out + g_commit * w * 2/(N d) * sum_q r_{q+1}; gcb[q, idx] -= g_commit * 2/(N d) * r_{q+1}."""
+        lib = _lib.load()
+        xf = x.detach()
+        if xf.dtype != torch.float32:
+            xf = xf.float()
+        x3, N, L, sb, sl, sd = _frame_addressing(xf)
+        dev = x3.device
+        gx = torch.empty_strided(x3.shape, x3.stride(), dtype=torch.float32, device=dev) if need_x else None
+        go = add_later = None
+        if need_x and g_out is not None:
+            g3 = g_out.reshape(x3.shape)
+            if g3.dtype == torch.float32 and g3.stride() == x3.stride() and g3.data_ptr() % 16 == 0:
+                go = g3                      # same addressing as x: fused into the kernel
+            else:
+                add_later = g3
+        gcb = torch.zeros_like(cb) if need_cb else None
+        gc = g_commit.detach().to(device=dev, dtype=torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(lib.rvq_backward(_ptr(x3), N, L, sb, sl, sd, self.dim, nq, self.K, _ptr(cb), _ptr(idx.reshape(-1, nq)),
+                                        _ptr(go), _ptr(gc), self.commitment_weight, 1.0 if need_cb else 0.0,
+                                        _ptr(gx), _ptr(gcb), _stream()), "rvq_backward")
+        if gx is not None:
+            if add_later is not None:
+                gx = gx + add_later
+            gx = gx.reshape(x.shape).to(x.dtype)
+        return gx, gcb
 
     def forward(self, x, n=None, update_codebook=False, prioritize_early=False):
         if prioritize_early:

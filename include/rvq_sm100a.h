@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RVQ_ABI_VERSION 5
+#define RVQ_ABI_VERSION 6
 
 typedef enum {
     RVQ_OK = 0,
@@ -143,6 +143,19 @@ int rvq_reseed_gather(const float* x, long long N, long long L, long long stride
                       long long frame_offset, long long frames_total, float* rep, void* stream);
 int rvq_reseed_apply(float* cb, float* ema_count, float* ema_sum, const float* rep, const int* k_valid,
                      int nq_use, int K, int d, float cutoff, float reset_count, int* n_replaced, void* stream);
+
+/* Backward of the quantizer call for autograd (the loss is taken on the decoder output plus the commit loss,
+ * /root/reference/networks/training.py:336,344-346; codebooks are parameters for quantizer_class "base",
+ * /root/reference/config/training.yml:21).  With coef = *g_commit * 2 / (N d) and r_{q+1} the residual after stage q
+ * (re-walked from x, idx and cb in fp32 stage order):
+ *   gx[n, :]            = g_out[n, :] + coef * w_commit * sum_q r_{q+1}[n, :]      (straight-through + commit loss)
+ *   gcb[q, idx[n,q], :] += -coef * w_codebook * r_{q+1}[n, :]                       (codebook loss; caller zeroes)
+ * x, g_out (nullable = zeros), gx (nullable) share the frame addressing of rvq_encode; g_commit is a DEVICE scalar
+ * (nullable = 0: no host synchronisation); gcb [nq_use.., K, d] nullable.                                     */
+int rvq_backward(const float* x, long long N, long long L, long long stride_b, long long stride_l,
+                 long long stride_d, int d, int nq_use, int K, const float* cb, const long long* idx,
+                 const float* g_out, const float* g_commit, float w_commit, float w_codebook, float* gx, float* gcb,
+                 void* stream);
 
 /* Bring-up / test hook: run ONE stage of the tensor-core filter for the first 128 frames of x
  * (contiguous [128, d]) and write the approximate scaled scores fp32 [128, Kpad] and the per-row

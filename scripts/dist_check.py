@@ -15,12 +15,27 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(11)
 nq, K, d, N = 4, 1024, 256, 1 << 16
-m = ResidualQuantizer(nq, d, "ema", K).to(dev).train()
+
+
+def force_stale(model):
+    """A few far-away codes with a low EMA count: never selected, so the update must re-seed them - from frames that
+    live on different ranks (the replacement vectors travel in the same all-reduce as the statistics)."""
+    with torch.no_grad():
+        for q, k in ((0, 5), (1, 1023), (3, 512), (3, 31)):
+            model.codebooks[q, k] = 100.0
+            model.ema_sum[q, k] = 100.0
+            model.ema_count[q, k] = 0.05
+    return model
+
+
+m = force_stale(ResidualQuantizer(nq, d, "ema", K)).to(dev).train()        # defaults: SOM spreading + re-seeding on
 x = torch.randn(N, d, device=dev)                      # same seed on every rank -> same full batch
 shard = x[rank * N // world:(rank + 1) * N // world]
+replaced = []
 for step in range(2):
     with torch.no_grad():
         _, idx, commit = m(shard, None, update_codebook=True)
+    replaced.append(m.n_replaced.tolist())
 torch.cuda.synchronize()
 cb = m.codebooks.clone()
 gathered = [torch.empty_like(cb) for _ in range(world)]
@@ -30,12 +45,16 @@ dist.barrier()
 dist.destroy_process_group()                           # single-GPU reference below must not all-reduce
 if rank == 0:
     torch.manual_seed(11)
-    ref = ResidualQuantizer(nq, d, "ema", K).to(dev).train()
+    ref = force_stale(ResidualQuantizer(nq, d, "ema", K)).to(dev).train()
+    ref_replaced = []
     for step in range(2):
         with torch.no_grad():
             ref(x, None, update_codebook=True)
+        ref_replaced.append(ref.n_replaced.tolist())
     err = (ref.codebooks - cb).abs().max().item()
     cnt_err = (ref.ema_count - m.ema_count).abs().max().item()
     print(f"world={world} replicas_bit_identical={identical} max|codebook diff vs single GPU|={err:.3e} "
           f"max|ema_count diff|={cnt_err:.3e}")
+    print(f"codes re-seeded per step and stage: sharded {replaced} single GPU {ref_replaced}")
     assert identical and err < 1e-3 and cnt_err < 1e-3
+    assert replaced == ref_replaced and sum(replaced[0]) >= 4

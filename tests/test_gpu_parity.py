@@ -205,15 +205,24 @@ def test_eval_mode_does_not_update():
     assert torch.equal(before, m.codebooks)
 
 
+@pytest.mark.parametrize("strided", [False, True])
 @pytest.mark.parametrize("cls", ["ema", "base"])
-def test_autograd_matches_oracle(cls):
+def test_autograd_matches_oracle(cls, strided):
+    """rvq_backward (straight-through + commit loss [+ codebook loss for "base"]) against torch autograd on the oracle;
+    strided = the reference's (B, L, d) view of a (B, d, L) encoder output (vae.py:313)."""
     nq, K, d = 3, 256, 64
     m = make(nq, K, d, cls=cls)
     ref = O.ResidualQuantizerRef(nq, d, cls, K)
     with torch.no_grad():
         ref.codebooks.copy_(m.codebooks.detach().cpu())
-    x = torch.randn(4, 50, d, device="cuda", requires_grad=True)
-    xr = x.detach().cpu().requires_grad_(True)
+    if strided:
+        leaf = torch.randn(4, d, 50, device="cuda", requires_grad=True)
+        x = leaf.permute(0, 2, 1)
+        rleaf = leaf.detach().cpu().requires_grad_(True)
+        xr = rleaf.permute(0, 2, 1)
+    else:
+        leaf = x = torch.randn(4, 50, d, device="cuda", requires_grad=True)
+        rleaf = xr = x.detach().cpu().requires_grad_(True)
     w = torch.randn(4, 50, d, device="cuda")
     out, idx, commit = m(x)
     (out * w).sum().add(3.0 * commit).backward()
@@ -222,9 +231,17 @@ def test_autograd_matches_oracle(cls):
     assert torch.equal(idx.cpu(), ridx)
     assert torch.allclose(commit.cpu(), rcommit, rtol=1e-5)
     assert torch.allclose(out.detach().cpu(), ro.detach(), atol=1e-5)
-    assert torch.allclose(x.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(leaf.grad.cpu(), rleaf.grad, rtol=1e-4, atol=1e-6)
     if cls == "base":
         assert torch.allclose(m.codebooks.grad.cpu(), ref.codebooks.grad, rtol=1e-4, atol=1e-6)
+    # commit loss alone (no gradient arriving through x_quantized), partial stages
+    leaf.grad = None
+    rleaf.grad = None
+    _, _, c2 = m(x, 2)
+    c2.backward()
+    _, _, rc2 = ref(xr, 2)
+    rc2.backward()
+    assert torch.allclose(leaf.grad.cpu(), rleaf.grad, rtol=1e-4, atol=1e-7)
 
 
 def test_dequantize_and_stage_api():
