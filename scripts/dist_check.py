@@ -21,10 +21,15 @@ def force_stale(model):
     """A few far-away codes with a low EMA count: never selected, so the update must re-seed them - from frames that
     live on different ranks (the replacement vectors travel in the same all-reduce as the statistics)."""
     with torch.no_grad():
-        for q, k in ((0, 5), (1, 1023), (3, 512), (3, 31)):
-            model.codebooks[q, k] = 100.0
-            model.ema_sum[q, k] = 100.0
-            model.ema_count[q, k] = 0.05
+        # a dead 3 x 3 block of the 32 x 32 map: the SOM neighbourhood rescues its corners (two live neighbours each),
+        # the centre and the edges stay below the cutoff
+        for q in (0, 3):
+            for y in (10, 11, 12):
+                for xg in (10, 11, 12):
+                    k = y * 32 + xg
+                    model.codebooks[q, k] = 100.0
+                    model.ema_sum[q, k] = 100.0
+                    model.ema_count[q, k] = 0.05
     return model
 
 
