@@ -164,36 +164,41 @@ def test_ragged_codebook_sizes():
     assert int(i2[:, 1].max()) < 300 and int(i2[:, 2].max()) < 64
 
 
-@pytest.mark.parametrize("algo", ["tensor", "exact_scan"])
-def test_ema_update_matches_oracle(algo):
+@pytest.mark.parametrize("algo,d", [("tensor", 128), ("exact_scan", 128), ("tensor", 256), ("tensor", 512),
+                                    ("tensor", 192), ("tensor", 64)])
+def test_ema_update_matches_oracle(algo, d):
     """The north-star update (counts + summed vectors -> EMA refresh), SOM spreading and re-seeding switched off;
-    tests/test_gpu_codebook_maintenance.py covers them."""
-    nq, K, d, N = 3, 512, 128, 20000
+    tests/test_gpu_codebook_maintenance.py covers them.  d = 128 / 64: TMEM-resident kernel; 192 / 256 / 512: generic
+    kernel.  Indices are adjudicated against the oracle (fp32 near-ties are legal); the statistics and the refreshed
+    state are then checked teacher-forced, i.e. against the oracle's update computed from the GPU's own indices, so
+    that one legal near-tie does not show up as a count difference of 0.01."""
+    nq, K, N = 3, 512, 20000
     m = make(nq, K, d, algo=algo)
     m.use_som, m.vq_cutoff_freq = False, 0.0
-    ref = O.ResidualQuantizerRef(nq, d, "ema", K, use_som=False, vq_cutoff_freq=0)
-    with torch.no_grad():
-        ref.codebooks.copy_(m.codebooks.cpu())
-        ref.ema_sum.copy_(m.ema_sum.cpu())
-        ref.ema_count.copy_(m.ema_count.cpu())
     m.train()
-    ref.train()
     for step in range(3):
+        cbs = cbs_of(m)
+        cnt0, sum0 = m.ema_count.cpu().clone(), m.ema_sum.cpu().clone()
         x = torch.randn(N, d, device="cuda")
         with torch.no_grad():
             _, idx, c = m(x, None, update_codebook=True)
-            _, ridx, rc = ref(x.cpu(), None, update_codebook=True)
         torch.cuda.synchronize()
-        same = (idx.cpu() == ridx).all(dim=1).float().mean()
-        assert same > 0.999
-        cnt = m.ema_count.cpu()
-        assert torch.allclose(cnt, ref.ema_count, rtol=1e-5, atol=1e-5)
-        assert torch.allclose(m.ema_sum.cpu(), ref.ema_sum, rtol=1e-4, atol=1e-4)
-        assert torch.allclose(m.codebooks.cpu(), ref.codebooks.detach(), rtol=1e-4, atol=1e-4)
-    # statistics identity: counts sum to N per stage
-    flat = m.last_stats
-    cnts = flat[nq * K * d: nq * K * (d + 1)].reshape(nq, K)
-    assert torch.allclose(cnts.sum(1).cpu(), torch.full((nq,), float(N)))
+        xc, ic = x.cpu(), idx.cpu()
+        adj = O.adjudicate_indices(xc, cbs, ic)
+        assert adj["n_illegal"] == 0 and adj["n_mismatch"] <= 12, adj
+        res = O.stage_residuals_from_indices(xc, cbs, ic)
+        flat = m.last_stats.cpu()
+        for q in range(nq):
+            cnt, sm = O.ema_stats_ref(res[q], ic[:, q], K)
+            assert torch.equal(flat[nq * K * d + q * K: nq * K * d + (q + 1) * K], cnt)              # counts are exact
+            assert torch.allclose(flat[q * K * d:(q + 1) * K * d].reshape(K, d), sm, rtol=1e-4, atol=1e-4)
+            ncb, nc, ns = O.ema_finalize_ref(cbs[q], cnt0[q], sum0[q], cnt, sm)
+            assert torch.allclose(m.ema_count[q].cpu(), nc, rtol=1e-6, atol=1e-6)
+            assert torch.allclose(m.ema_sum[q].cpu(), ns, rtol=1e-4, atol=1e-4)
+            assert torch.allclose(m.codebooks[q].cpu(), ncb, rtol=1e-4, atol=1e-4)
+        # commit loss of the call = sum over stages of mean squared residual after the stage
+        rc = sum(float((res[q + 1].double() ** 2).mean()) for q in range(nq))
+        assert abs(float(c) - rc) <= 1e-5 * rc
 
 
 def test_eval_mode_does_not_update():
