@@ -191,10 +191,13 @@ def test_ema_update_matches_oracle(algo, d):
         for q in range(nq):
             cnt, sm = O.ema_stats_ref(res[q], ic[:, q], K)
             assert torch.equal(flat[nq * K * d + q * K: nq * K * d + (q + 1) * K], cnt)              # counts are exact
-            assert torch.allclose(flat[q * K * d:(q + 1) * K * d].reshape(K, d), sm, rtol=1e-4, atol=1e-4)
+            # sums: fp32 atomics add in arbitrary order -> absolute error ~ count * ulp(max |r|) per code
+            tol = (2e-6 * cnt * float(res[q].abs().max()) + 1e-5)[:, None]
+            gsum = flat[q * K * d:(q + 1) * K * d].reshape(K, d)
+            assert bool(((gsum - sm).abs() <= tol).all()), float((gsum - sm).abs().max())
             ncb, nc, ns = O.ema_finalize_ref(cbs[q], cnt0[q], sum0[q], cnt, sm)
             assert torch.allclose(m.ema_count[q].cpu(), nc, rtol=1e-6, atol=1e-6)
-            assert torch.allclose(m.ema_sum[q].cpu(), ns, rtol=1e-4, atol=1e-4)
+            assert bool(((m.ema_sum[q].cpu() - ns).abs() <= 0.01 * tol + 1e-6 * ns.abs()).all())
             assert torch.allclose(m.codebooks[q].cpu(), ncb, rtol=1e-4, atol=1e-4)
         # commit loss of the call = sum over stages of mean squared residual after the stage
         rc = sum(float((res[q + 1].double() ** 2).mean()) for q in range(nq))
