@@ -12,7 +12,7 @@ from audio_generation_b200 import ResidualQuantizer
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 wl = bench.WORKLOADS[name]
 nq, K, d, N = wl["nq"], wl["K"], wl["d"], min(wl["frames"], 1 << 18)
-q = ResidualQuantizer(nq, d, "ema", K)
+q = ResidualQuantizer(nq, d, "ema", K, use_som=False, vq_cutoff_freq=0)
 with torch.no_grad():
     q.codebooks.copy_(bench.synth_codebooks(nq, K, d))
 upd = "--update" in sys.argv
