@@ -144,21 +144,35 @@ __device__ __forceinline__ void apply_seg(uint8_t* smem_a, const RTile& rt, int 
 // the pass), so the converted row is written in the same pass; the error bound uses the exact new norm.
 // All 32 lanes of the warp must call this together (8-lane shuffles with a full mask); `active` gates effects.
 //   next_q_abs < 0 : last stage (no operand for a next stage)
+// per-job constants of apply_row (read from the stage metadata ONCE per job, not per row: the metadata loads were a
+// second global round trip in front of every row's residual / code loads)
+struct StageC {
+    float sb, cnmax, cmax_q;  // 2^b and max ||c||_2 of the NEXT stage, max |c| of this stage
+};
+__device__ __forceinline__ StageC load_stage_consts(const EncParams& p, int q_abs, int next_q_abs) {
+    StageC sc{1.f, 0.f, 0.f};
+    if (next_q_abs >= 0) {
+        const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
+        sc.sb = mq[0];
+        sc.cnmax = mq[1];
+        sc.cmax_q = p.cb_meta[(size_t)q_abs * META_STRIDE + 2];
+    }
+    return sc;
+}
+
 __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
                                           int row, bool active, bool row_valid, int kwin, int q_abs, int next_q_abs,
-                                          int sub, float* sq_out) {
+                                          int sub, float* sq_out, const StageC& sc) {
     const int d = p.d;
     float sq = 0.f, amax = 0.f;
-    float sa = 0.f, sb = 1.f, cnmax = 0.f;
+    float sa = 0.f;
+    const float sb = sc.sb, cnmax = sc.cnmax;
     int a = 0, b = 0;
     bool force_exact = false;
     const bool write_a = next_q_abs >= 0;
     if (write_a) {
-        const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
-        sb = mq[0];
-        cnmax = mq[1];
         b = ilog2f_floor(sb);
-        const float bound = misc->row_amax[sl][row] + p.cb_meta[(size_t)q_abs * META_STRIDE + 2];
+        const float bound = misc->row_amax[sl][row] + sc.cmax_q;
         a = pick_row_exp(bound, b, force_exact);
         sa = exp2i(a);
     }
@@ -285,12 +299,16 @@ __device__ __forceinline__ void apply_two_rows_128(const EncParams& p, Misc* mis
 // Stage-0 initialisation of one frame by an 8-lane group: x -> residual scratch, exact max -> operand scale,
 // fp16 operand row and row constants of the first stage (two passes: the scale needs the row maximum).
 __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
-                                         int row, const float* __restrict__ xr, bool row_valid, int sub) {
+                                         int row, const float* __restrict__ xr, bool row_valid, int sub,
+                                         bool stream_x) {
     const int d = p.d;
     float sq = 0.f, amax = 0.f;
 #pragma unroll 2
     for (int c = sub * 4; c < d; c += 32) {
-        const float4 v = row_valid ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // x streams through L2 once (evict-first) so that it does not push the residual scratch out
+        const float4 v = row_valid ? (stream_x ? __ldcs(reinterpret_cast<const float4*>(xr + c))
+                                               : *reinterpret_cast<const float4*>(xr + c))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(rt.at(row, c)) = v;
         sq = fmaf(v.x, v.x, sq);
         sq = fmaf(v.y, v.y, sq);
@@ -573,7 +591,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                 const long long n = n0 + row;
                 const float* xr = row_major ? p.x + (n < p.N ? p.ad.row(n) : 0) : rt.at(row, 0);
-                init_row(p, misc, a_tile, rt, sl, row, xr, row_major ? n < p.N : true, sub);
+                init_row(p, misc, a_tile, rt, sl, row, xr, row_major ? n < p.N : true, sub, row_major);
             }
             fence_proxy_async_smem();
             mbar_arrive(&misc->a_ready[sl]);
@@ -596,6 +614,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             t_wait += t1 - t0;
             const int next_q_abs = (q + 1 < nq) ? q_abs + 1 : -1;
             const float* cbq = p.cb + (size_t)q_abs * p.K * d;
+            const StageC sc = load_stage_consts(p, q_abs, next_q_abs);
             // ---------------- classify the frames: certified (one candidate), re-rank list, exact-scan list
             const long long ts0 = clock64();
             const int Kv_q = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
@@ -657,7 +676,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             auto post_row = [&](int row, bool active, int kwin, float sq) {
                 const long long n = n0 + row;
                 if (active && sub == 0 && n < p.N) {
-                    p.idx[n * nq + q] = kwin;
+                    __stcs(p.idx + n * nq + q, (long long)kwin);
                     commit_local += (double)sq;
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
@@ -680,7 +699,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                     const bool active = misc->win[sl][row] >= 0;
                     const int kwin = active ? misc->win[sl][row] : 0;
                     float sq;
-                    apply_row(p, misc, a_tile, rt, sl, row, active, n0 + row < p.N, kwin, q_abs, next_q_abs, sub, &sq);
+                    apply_row(p, misc, a_tile, rt, sl, row, active, n0 + row < p.N, kwin, q_abs, next_q_abs, sub, &sq, sc);
                     post_row(row, active, kwin, sq);
                 }
             }
@@ -719,9 +738,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         if (bk < 0 || bk >= Kv) bk = 0;
                         const long long n = n0 + row;
                         float sq;
-                        apply_row(p, misc, a_tile, rt, sl, row, lane < 8, n < p.N, bk, q_abs, next_q_abs, sub, &sq);
+                        apply_row(p, misc, a_tile, rt, sl, row, lane < 8, n < p.N, bk, q_abs, next_q_abs, sub, &sq, sc);
                         if (lane == 0 && n < p.N) {
-                            p.idx[n * nq + q] = bk;
+                            __stcs(p.idx + n * nq + q, (long long)bk);
                             atomicAdd(&misc->commit_acc[q], (double)sq);
                             if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + bk, 1.f);
                         }
@@ -745,14 +764,14 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         if (n < p.N) {
                             const long long off = p.ad.row(n);
                             for (int c = sub * 4; c < d; c += 32) {
-                                const float4 xv = *reinterpret_cast<const float4*>(p.x + off + c);
+                                const float4 xv = __ldcs(reinterpret_cast<const float4*>(p.x + off + c));
                                 const float4 rv = *reinterpret_cast<const float4*>(rt.at(row, c));
                                 float4 o;
                                 o.x = xv.x - rv.x;
                                 o.y = xv.y - rv.y;
                                 o.z = xv.z - rv.z;
                                 o.w = xv.w - rv.w;
-                                *reinterpret_cast<float4*>(p.xq + off + c) = o;
+                                __stcs(reinterpret_cast<float4*>(p.xq + off + c), o);
                             }
                         }
                     }

@@ -207,10 +207,16 @@ def main():
     # EMA workloads start from synthetic codebooks that the first updates pull towards the data (near-degenerate
     # codebooks, many exact re-ranks): time the steady state, not that transient
     n_warm = max(args.warmup, 40 if wl["update"] else 3)
+    # the clock sampler (nvidia-smi -lms) starts BEFORE the warm-up: its start-up (NVML initialisation) was seen to
+    # stall kernel launches for tens of milliseconds when it fell into the timed region; rows are filtered by time
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0.record()
+    out = None
     for _ in range(n_warm):
-        step()
+        out = step()          # held like in the timed loop: the allocator reaches its steady state here
     w1.record()
     torch.cuda.synchronize()
     # ... and keep warming until the GPU has seen ~0.4 s of this kernel (a box fresh out of idle needs more than a
@@ -220,13 +226,8 @@ def main():
     if world > 1:
         dist.all_reduce(extra, op=dist.ReduceOp.MAX)
     for _ in range(min(int(extra.item()), 2000)):
-        step()
+        out = step()
         n_warm += 1
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    time.sleep(0.2)              # every rank: a late rank 0 would make the others wait inside their timed region
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
