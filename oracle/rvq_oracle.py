@@ -17,6 +17,11 @@ no golden vectors.  This file therefore restates
   constants of the lineage the reference credits (``README.md:26-27``: Jukebox /
   rosinality VQ-VAE: decay 0.99, Laplace smoothing eps 1e-5).
 
+* the codebook maintenance behind the constructor's ``use_som`` / ``som_kernel_type`` / ``vq_cutoff_freq``
+  keywords: SOM neighbourhood of the statistics after the paper the reference cites
+  (``README.md:10``, arXiv 2302.07950) and dead-code re-seeding of the Jukebox / lucidrains lineage - both
+  entirely ASSUMED semantics, with a stated hash for the frame choice so that they are testable.
+
 Every choice not pinned by a call site is marked ASSUMED.
 Independent cross-check: ``tests/test_oracle.py`` compares the index chain with
 HuggingFace ``EncodecResidualVectorQuantizer.encode`` (an unrelated implementation
