@@ -11,7 +11,11 @@
 namespace rvq {
 
 // ------------------------------------------------------------------------------------------ K0
-// one block per stage: max |c| over the valid codes -> meta[q] = {2^b, 0 (cnmax, filled by k0_convert), cmax, Kv}
+// K0_SPLIT blocks per stage: max |c| over the valid codes -> meta[q] = {2^b, 0 (cnmax, filled by k0_convert), cmax, Kv}.
+// Every block folds its slice into meta[q][2] with an integer atomicMax (non-negative floats order like ints; NaNs are
+// dropped by fmaxf before); the block that takes the last ticket of the stage (meta[q][5], zeroed by the caller
+// together with meta[q][2]) writes the derived entries.  One block per stage took 119 us per update step on C3.
+constexpr int K0_SPLIT = 16;
 __global__ void k0_stage_max(const float* __restrict__ cb, const int* __restrict__ k_valid, int K, int d,
                              float* __restrict__ meta) {
     const int q = blockIdx.x;
@@ -19,7 +23,8 @@ __global__ void k0_stage_max(const float* __restrict__ cb, const int* __restrict
     const float* base = cb + (size_t)q * K * d;
     const size_t n = (size_t)Kv * d;
     float m = 0.f;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(base[i]));
+    for (size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.y * blockDim.x)
+        m = fmaxf(m, fabsf(base[i]));
     __shared__ float red[32];
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -29,12 +34,18 @@ __global__ void k0_stage_max(const float* __restrict__ cb, const int* __restrict
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (threadIdx.x == 0) {
             float* mq = meta + q * META_STRIDE;
-            mq[0] = exp2i(code_scale_exp(m));
-            mq[1] = 0.f;
-            mq[2] = m;
-            mq[3] = (float)Kv;
-            mq[4] = (float)gridDim.x;  // stages prepared: locates the norm slices behind the norms
-            mq[5] = mq[6] = mq[7] = 0.f;
+            atomicMax(reinterpret_cast<int*>(mq + 2), __float_as_int(m));
+            __threadfence();
+            const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(mq + 5), 1u);
+            if (ticket == gridDim.y - 1) {
+                __threadfence();
+                const float mall = __int_as_float(atomicMax(reinterpret_cast<int*>(mq + 2), 0));
+                mq[0] = exp2i(code_scale_exp(mall));
+                mq[1] = 0.f;
+                mq[3] = (float)Kv;
+                mq[4] = (float)gridDim.x;  // stages prepared: locates the norm slices behind the norms
+                mq[5] = mq[6] = mq[7] = 0.f;
+            }
         }
     }
 }
@@ -292,7 +303,8 @@ extern "C" int rvq_prepare_codebooks(const float* cb, const int* k_valid, int nq
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int Kpad = round_up(K, CHUNK_N);
-    k0_stage_max<<<nq, 1024, 0, st>>>(cb, k_valid, K, d, cb_meta);
+    RVQ_CUDA(cudaMemsetAsync(cb_meta, 0, sizeof(float) * (size_t)nq * META_STRIDE, st));
+    k0_stage_max<<<dim3((unsigned)nq, K0_SPLIT), 512, 0, st>>>(cb, k_valid, K, d, cb_meta);
     const long long warps = (long long)nq * Kpad;
     const int block = 256;
     const long long grid = (warps * 32 + block - 1) / block;

@@ -32,6 +32,8 @@ WORKLOADS = {
                      "stale-code re-seeding (vq_cutoff_freq=1) every step"),
     "c4s": dict(nq=32, K=4096, d=512, frames=1 << 17, update=False,
                 desc="BASELINE configs[3] shape (32 x 4096 codes, d=512), 128K frames per GPU"),
+    "c4": dict(nq=32, K=4096, d=512, frames=1 << 21, update=False,
+               desc="BASELINE configs[3] at full size: 32 x 4096 codes, d=512, 2M frames per GPU (16M frames on 8 GPUs)"),
     "c5q": dict(nq=8, K=1024, d=512, frames=1 << 18, update=False,
                 desc="reference model default quantizer (8 x 1024, d=512), 256K frames per GPU"),
 }

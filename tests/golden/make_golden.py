@@ -46,6 +46,36 @@ def small():
     print("rvq_small.npz", idx.shape, commit)
 
 
+def maint():
+    """codebook_maint.npz: SOM neighbourhood spreading and stale-code re-seeding on a small seeded problem
+    (semantics ASSUMED, see oracle/rvq_oracle.py)."""
+    torch.manual_seed(20261019)
+    K, d, N, q, seed = 24, 64, 96, 2, 0x1234ABCD
+    h, w = O.approximate_square_root(K)
+    sm = torch.randn(K, d)
+    cnt = torch.randint(0, 9, (K,)).float()
+    out = {}
+    for name, t in (("hard", 3), ("gaussian", 0), ("gaussian", 40)):
+        radius, wts = O.som_weights(name, t)
+        osm, ocnt = O.som_spread_ref(sm.numpy(), cnt.numpy(), h, w, radius, wts)
+        out[f"som_{name}_{t}_sum"] = osm
+        out[f"som_{name}_{t}_cnt"] = ocnt
+        out[f"som_{name}_{t}_w"] = np.asarray(wts)
+    r_q = torch.randn(N, d)
+    rep = O.reseed_vectors_ref(r_q, q, K, seed)
+    rep_rank1 = O.reseed_vectors_ref(r_q[N // 2:], q, K, seed, frame_offset=N // 2, frames_total=N)
+    frames = np.array([O.reseed_frame_ref(seed, q, K, k, N) for k in range(K)])
+    cb = torch.randn(K, d)
+    ema_count = torch.rand(K) * 2.0
+    ema_sum = torch.randn(K, d)
+    ncb, nc, ns, n_rep = O.reseed_apply_ref(cb, ema_count, ema_sum, rep, 1.0, 1.0)
+    np.savez_compressed(os.path.join(HERE, "codebook_maint.npz"), K=K, d=d, N=N, q=q, seed=seed, grid=np.array([h, w]),
+                        sum=sm.numpy(), cnt=cnt.numpy(), r_q=r_q.numpy(), rep=rep.numpy(), rep_rank1=rep_rank1.numpy(),
+                        frames=frames, cb=cb.numpy(), ema_count=ema_count.numpy(), ema_sum=ema_sum.numpy(),
+                        new_cb=ncb.numpy(), new_count=nc.numpy(), new_sum=ns.numpy(), n_replaced=n_rep, **out)
+    print("codebook_maint.npz", frames[:6], n_rep)
+
+
 def c1():
     import yaml
     from scipy.io import wavfile
@@ -97,4 +127,5 @@ def c1():
 
 if __name__ == "__main__":
     small()
+    maint()
     c1()

@@ -166,3 +166,49 @@ def test_module_update_with_som_and_reseed_matches_oracle(kernel):
         m2(x, None, update_codebook=True)
     assert int(m2.update_steps) == 4
     assert torch.allclose(m.codebooks, m2.codebooks, rtol=1e-4, atol=1e-5)
+
+
+def test_kernels_reproduce_the_golden_fixture():
+    """The committed vectors of tests/golden/codebook_maint.npz through the C ABI, bit for bit."""
+    import os
+    from audio_generation_b200 import _lib
+    lib = _lib.load()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "codebook_maint.npz"))
+    K, d, N, q, seed = int(z["K"]), int(z["d"]), int(z["N"]), int(z["q"]), int(z["seed"])
+    h, w = (int(v) for v in z["grid"])
+    sm = torch.from_numpy(z["sum"]).cuda().unsqueeze(0).contiguous()
+    cnt = torch.from_numpy(z["cnt"]).cuda().unsqueeze(0).contiguous()
+    for name, t in (("hard", 3), ("gaussian", 0), ("gaussian", 40)):
+        wts = z[f"som_{name}_{t}_w"]
+        radius = (wts.shape[0] - 1) // 2
+        wf = [float(v) for v in wts.reshape(-1)]
+        osm, ocnt = torch.empty_like(sm), torch.empty_like(cnt)
+        _lib.check(lib.rvq_som_spread(_p(sm), _p(cnt), _p(osm), _p(ocnt), (C.c_int * 2)(h, w), 1, K, d, radius,
+                                      (C.c_float * len(wf))(*wf), _s()), "rvq_som_spread")
+        assert np.array_equal(osm[0].cpu().numpy(), z[f"som_{name}_{t}_sum"])
+        assert np.array_equal(ocnt[0].cpu().numpy(), z[f"som_{name}_{t}_cnt"])
+    # re-seeding of stage q: stages before it have all-zero codebooks, so the stage-q residual is x itself
+    nq = q + 1
+    cb = torch.zeros(nq, K, d, device="cuda")
+    x = torch.from_numpy(z["r_q"]).cuda().contiguous()
+    idx = torch.zeros(N, nq, dtype=torch.int64, device="cuda")
+    rep = torch.full((nq, K, d), 9.0, device="cuda")
+    _lib.check(lib.rvq_reseed_gather(_p(x), N, N, 0, d, 1, d, nq, K, _p(cb), _p(idx), None, 0.99, 1.0, seed, 0, N,
+                                     _p(rep), _s()), "rvq_reseed_gather")
+    assert np.array_equal(rep[q].cpu().numpy(), z["rep"])
+    half = x[N // 2:].contiguous()
+    _lib.check(lib.rvq_reseed_gather(_p(half), N - N // 2, N - N // 2, 0, d, 1, d, nq, K, _p(cb), _p(idx[N // 2:].contiguous()),
+                                     None, 0.99, 1.0, seed, N // 2, N, _p(rep), _s()), "rvq_reseed_gather")
+    assert np.array_equal(rep[q].cpu().numpy(), z["rep_rank1"])
+    cbq = torch.zeros(nq, K, d, device="cuda")
+    ec = torch.full((nq, K), 7.0, device="cuda")
+    es = torch.zeros(nq, K, d, device="cuda")
+    cbq[q], ec[q], es[q] = torch.from_numpy(z["cb"]).cuda(), torch.from_numpy(z["ema_count"]).cuda(), torch.from_numpy(z["ema_sum"]).cuda()
+    repf = torch.zeros(nq, K, d, device="cuda")
+    repf[q] = torch.from_numpy(z["rep"]).cuda()
+    nrep = torch.zeros(nq, dtype=torch.int32, device="cuda")
+    _lib.check(lib.rvq_reseed_apply(_p(cbq), _p(ec), _p(es), _p(repf), None, nq, K, d, 1.0, 1.0, _p(nrep), _s()),
+               "rvq_reseed_apply")
+    assert nrep.tolist() == [0] * q + [int(z["n_replaced"])]
+    assert np.array_equal(cbq[q].cpu().numpy(), z["new_cb"]) and np.array_equal(ec[q].cpu().numpy(), z["new_count"])
+    assert np.array_equal(es[q].cpu().numpy(), z["new_sum"])

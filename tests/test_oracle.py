@@ -189,3 +189,32 @@ def test_module_update_with_som_and_reseed_cpu():
     n = O.reseed_frame_ref(m.reseed_seed, 0, 16, 5, 64)
     assert float(m.ema_count[0, 5]) == 1.0 and torch.equal(m.codebooks[0, 5], x[n])      # stage 0 residual = x
     assert torch.equal(m.ema_sum[0, 5], x[n])
+
+
+def test_oracle_reproduces_codebook_maintenance_fixture():
+    """tests/golden/codebook_maint.npz (made by tests/golden/make_golden.py:maint) pins the SOM spreading, the frame
+    choice of the re-seeding and the re-seeded state."""
+    import numpy as np
+    z = np.load(os.path.join(GOLD, "codebook_maint.npz"))
+    K, d, N, q, seed = int(z["K"]), int(z["d"]), int(z["N"]), int(z["q"]), int(z["seed"])
+    h, w = (int(v) for v in z["grid"])
+    assert (h, w) == O.approximate_square_root(K)
+    for name, t in (("hard", 3), ("gaussian", 0), ("gaussian", 40)):
+        radius, wts = O.som_weights(name, t)
+        assert np.array_equal(np.asarray(wts), z[f"som_{name}_{t}_w"])
+        osm, ocnt = O.som_spread_ref(z["sum"], z["cnt"], h, w, radius, wts)
+        assert np.array_equal(osm, z[f"som_{name}_{t}_sum"]) and np.array_equal(ocnt, z[f"som_{name}_{t}_cnt"])
+    assert [O.reseed_frame_ref(seed, q, K, k, N) for k in range(K)] == z["frames"].tolist()
+    r_q = torch.from_numpy(z["r_q"])
+    rep = O.reseed_vectors_ref(r_q, q, K, seed)
+    assert np.array_equal(rep.numpy(), z["rep"]) and np.array_equal(rep.numpy(), z["r_q"][z["frames"]])
+    # a rank holding the second half of the frames contributes exactly the vectors it owns, zeros elsewhere
+    r1 = O.reseed_vectors_ref(r_q[N // 2:], q, K, seed, frame_offset=N // 2, frames_total=N)
+    assert np.array_equal(r1.numpy(), z["rep_rank1"])
+    own = z["frames"] >= N // 2
+    assert np.array_equal(r1.numpy()[own], z["rep"][own]) and not r1.numpy()[~own].any()
+    ncb, nc, ns, n = O.reseed_apply_ref(torch.from_numpy(z["cb"]), torch.from_numpy(z["ema_count"]),
+                                        torch.from_numpy(z["ema_sum"]), rep, 1.0, 1.0)
+    assert n == int(z["n_replaced"]) == int((z["ema_count"] < 1.0).sum())
+    assert np.array_equal(ncb.numpy(), z["new_cb"]) and np.array_equal(nc.numpy(), z["new_count"])
+    assert np.array_equal(ns.numpy(), z["new_sum"])
