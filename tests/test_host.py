@@ -96,3 +96,35 @@ def test_product_path_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_host_side_of_codebook_maintenance_matches_the_oracle():
+    """The weights the module hands to rvq_som_spread (float32 after ctypes conversion) and the per-step seed of the
+    re-seeding are the oracle's, for both neighbourhood kernels over the whole annealing range."""
+    import ctypes as C
+    import numpy as np
+    from audio_generation_b200 import ResidualQuantizer
+    from audio_generation_b200 import quantizer as Q
+    from oracle import rvq_oracle as O
+    for kernel in ("hard", "gaussian"):
+        for t in (0, 1, 2, 7, 19, 20, 21, 100, 5000):
+            r, w = Q.som_weights(kernel, t)
+            ro, wo = O.som_weights(kernel, t)
+            assert r == ro and len(w) == (2 * r + 1) ** 2
+            as_f32 = np.array(list((C.c_float * len(w))(*w)), dtype=np.float32).reshape(2 * r + 1, 2 * r + 1)
+            assert np.array_equal(as_f32, wo), (kernel, t)
+    with pytest.raises(ValueError):
+        ResidualQuantizer(2, 64, "ema", 64, som_kernel_type="soft")
+    assert Q.approximate_square_root(1024) == O.approximate_square_root(1024) == (32, 32)
+    assert Q.approximate_square_root(300) == O.approximate_square_root(300) == (15, 20)
+    m = ResidualQuantizer(2, 64, "ema", 64, reseed_seed=77)
+    ref = O.ResidualQuantizerRef(2, 64, "ema", 64, reseed_seed=77)
+    for steps in (0, 1, 12345):
+        ref.update_steps.fill_(steps)
+        assert ((m.reseed_seed + steps * 0xD1B54A32D192ED03) & Q._M64) == ref.step_seed()
+    # absolute-count staleness on the host side (no GPU needed): ema_count starts at 1, cutoff 1 -> nothing stale
+    assert m.get_stale_clusters() == [0, 0]
+    m.ema_count[1, :5] = 0.5
+    assert m.get_stale_clusters() == [0, 5]
+    m.update_cutoff(new_cutoff=0.25)
+    assert m.get_stale_clusters() == [0, 0]
