@@ -1,6 +1,6 @@
-"""compute-sanitizer target for the third-session kernels: a training step with the SOM neighbourhood and
+"""Exercise script (compute-sanitizer is closed on this pool; run it plainly, the asserts are the check) for the third-session kernels: a training step with the SOM neighbourhood and
 stale-code re-seeding on (ragged codebook sizes, the reference's strided frame layout), the backward pass for both
-quantizer classes, the wire format.  compute-sanitizer --tool memcheck python scripts/memcheck_maintenance.py"""
+quantizer classes, the wire format.  python scripts/exercise_maintenance.py"""
 import os
 import sys
 
