@@ -143,6 +143,11 @@ class _RVQFunction(torch.autograd.Function):
         return gx, gcb, None, None, None
 
 
+def _forget_step_mirror(module, _incompatible_keys):
+    """load_state_dict post-hook: the host mirror of ``update_steps`` is re-read from the loaded buffer."""
+    module._steps_host = None
+
+
 class ResidualQuantizer(nn.Module):
     """Residual vector quantizer on B200 (see module docstring for the interface it mirrors)."""
 
@@ -179,7 +184,7 @@ class ResidualQuantizer(nn.Module):
         self.register_buffer("n_replaced", torch.zeros(self.num_quantizers, dtype=torch.int32),
                              persistent=False)                                     # codes re-seeded by the last update
         self._steps_host = None    # host mirror of update_steps (read back once, then counted on the host)
-        self.register_load_state_dict_post_hook(lambda mod, _keys: setattr(mod, "_steps_host", None))
+        self.register_load_state_dict_post_hook(_forget_step_mirror)
         self.quantizers = [_Stage(self, q) for q in range(self.num_quantizers)]
         self._derived = None       # (key, cb_op, cb_norm, cb_meta)
         self._ws = None

@@ -128,3 +128,22 @@ def test_host_side_of_codebook_maintenance_matches_the_oracle():
     assert m.get_stale_clusters() == [0, 5]
     m.update_cutoff(new_cutoff=0.25)
     assert m.get_stale_clusters() == [0, 0]
+
+
+def test_module_survives_pickle_and_deepcopy():
+    """torch.save(model) / copy.deepcopy keep the stage views bound to the copy and the load hook working."""
+    import copy
+    import io
+    from audio_generation_b200 import ResidualQuantizer
+    m = ResidualQuantizer(2, 64, "ema", [64, 48])
+    m.update_steps.fill_(9)
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    m3 = copy.deepcopy(m)
+    for c in (m2, m3):
+        assert c.quantizers[1]._p is c and c.codebook_sizes == [64, 48]
+        c._steps_host = 3
+        c.load_state_dict(m.state_dict())
+        assert c._steps_host is None and int(c.update_steps) == 9
