@@ -239,7 +239,9 @@ class ResidualQuantizer(nn.Module):
         """One flat fp32 buffer [nq K d sums | nq K counts | nq K d replacement vectors] = one all-reduce payload."""
         nq, K, d = self.num_quantizers, self.K, self.dim
         if self._stats is None or self._stats.device != device:
-            self._stats = torch.empty(2 * nq * K * d + nq * K, dtype=torch.float32, device=device)
+            # zeros once: the replacement-vector part of stages a partial call (n < num_quantizers) does not write
+            # travels through the all-reduce as zeros, not as uninitialised memory
+            self._stats = torch.zeros(2 * nq * K * d + nq * K, dtype=torch.float32, device=device)
             self._spread = torch.empty(nq * K * d + nq * K, dtype=torch.float32, device=device)
         flat = self._stats
         return flat, flat[: nq * K * d], flat[nq * K * d: nq * K * (d + 1)], flat[nq * K * (d + 1):]
