@@ -51,7 +51,9 @@ def build(force: bool = False, verbose: bool = True) -> Path:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    (CSRC / "ptxas_info.txt").write_text("\n".join(log))
+    # register / spill report of every kernel (compile times dropped: they would change the file on every build)
+    info = [ln for ln in "\n".join(log).splitlines() if "Compile time" not in ln]
+    (CSRC / "ptxas_info.txt").write_text("\n".join(info) + "\n")
     if verbose:
         print(f"built {LIB}")
     return LIB
