@@ -218,3 +218,34 @@ def test_oracle_reproduces_codebook_maintenance_fixture():
     assert n == int(z["n_replaced"]) == int((z["ema_count"] < 1.0).sum())
     assert np.array_equal(ncb.numpy(), z["new_cb"]) and np.array_equal(nc.numpy(), z["new_count"])
     assert np.array_equal(ns.numpy(), z["new_sum"])
+
+
+def test_codebook_maintenance_properties():
+    """Size-independent properties of the maintenance restatement: the neighbourhood is linear, reduces to the identity
+    for a centre-only kernel, conserves mass away from the border for the hard kernel; the frame choice of the
+    re-seeding is deterministic, in range and spread over the batch."""
+    import numpy as np
+    rng = np.random.default_rng(4)
+    h, w, d = 6, 9, 5
+    a, b = rng.standard_normal((h * w, d)).astype(np.float32), rng.standard_normal((h * w, d)).astype(np.float32)
+    ca, cb_ = rng.integers(0, 7, h * w).astype(np.float32), rng.integers(0, 7, h * w).astype(np.float32)
+    r, wt = O.som_weights("gaussian", 5)
+    sa, na = O.som_spread_ref(a, ca, h, w, r, wt)
+    sb, nb = O.som_spread_ref(b, cb_, h, w, r, wt)
+    sab, nab = O.som_spread_ref(a + b, ca + cb_, h, w, r, wt)
+    assert np.allclose(sab, sa + sb, atol=1e-5) and np.allclose(nab, na + nb, atol=1e-5)
+    ident = np.zeros((3, 3), dtype=np.float32)
+    ident[1, 1] = 1.0
+    s1, n1 = O.som_spread_ref(a, ca, h, w, 1, ident)
+    assert np.array_equal(s1, a) and np.array_equal(n1, ca)
+    # hard kernel, sigma = 0.25: a unit count in an interior cell spreads to 1 + 4 * 0.25 = 2 in total
+    one = np.zeros(h * w, dtype=np.float32)
+    one[3 * w + 4] = 1.0
+    _, n2 = O.som_spread_ref(np.zeros((h * w, d), np.float32), one, h, w, *O.som_weights("hard", 30))
+    assert abs(float(n2.sum()) - 2.0) < 1e-6 and int((n2 > 0).sum()) == 5
+    K, N = 1024, 600
+    fr = [O.reseed_frame_ref(99, 3, K, k, N) for k in range(K)]
+    assert fr == [O.reseed_frame_ref(99, 3, K, k, N) for k in range(K)] and 0 <= min(fr) and max(fr) < N
+    assert len(set(fr)) > 0.7 * N                      # 1024 draws over 600 frames hit most of them
+    assert fr != [O.reseed_frame_ref(100, 3, K, k, N) for k in range(K)]
+    assert fr != [O.reseed_frame_ref(99, 4, K, k, N) for k in range(K)]
