@@ -10,8 +10,13 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "librvq_sm100a.so"
 
+RVQ_ABI_VERSION = 7
 RVQ_ALGO_TENSOR = 0
 RVQ_ALGO_EXACT_SCAN = 1
+# kernel selectors / launch options of rvq_encode's `flags` (include/rvq_sm100a.h)
+RVQ_KERNELS = {"auto": 0x00, "generic": 0x10, "frame": 0x20, "tmem": 0x30}
+RVQ_FLAG_CLUSTER_SHIFT = 8
+RVQ_FLAG_COUNTERS = 0x1000
 
 _vp, _i, _ll, _sz, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_float
 
@@ -26,6 +31,7 @@ SIGNATURES = {
     "rvq_encode": (_i, [_vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                         _vp, _sz, _i, _vp]),
     "rvq_ema_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    "rvq_ema_counts": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp]),
     "rvq_dequantize": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _ll, _i, _i, _i, _i, C.POINTER(_f), _i, _vp, _vp]),
     "rvq_packed_bytes_per_frame": (_i, [_i, _i]),
     "rvq_pack_indices": (_i, [_vp, _ll, _i, _i, _vp, _vp]),

@@ -11,7 +11,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB = Path(__file__).resolve().parent / "librvq_sm100a.so"
-SOURCES = ["rvq_abi.cu", "rvq_aux.cu", "rvq_encode_tc.cu", "rvq_encode_tr.cu", "rvq_codebook.cu", "rvq_backward.cu"]
+SOURCES = ["rvq_abi.cu", "rvq_aux.cu", "rvq_encode_tc.cu", "rvq_encode_tr.cu", "rvq_encode_fr.cu", "rvq_codebook.cu", "rvq_backward.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "exact.cuh", "encode_common.cuh", "../../include/rvq_sm100a.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -37,11 +37,13 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = True) -> Path:
     if not force and not needs_build():
         return LIB
+    # extra -D switches for experiment builds (e.g. RVQ_NVCC_DEFS="-DRVQ_FR_PROFILE"): read at BUILD time only
+    extra = os.environ.get("RVQ_NVCC_DEFS", "").split()
     objs = []
     log = []
     for src in SOURCES:
         obj = CSRC / (src[:-3] + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(r.stderr)
         if r.returncode != 0:

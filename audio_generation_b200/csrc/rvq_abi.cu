@@ -1,7 +1,6 @@
 // rvq_abi.cu -- extern "C" entry points of librvq_sm100a.so (declared in include/rvq_sm100a.h):
 // argument checking, device gate, error state, dispatch to the kernels.  No torch types cross this file.
 #include <cstdarg>
-#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -27,13 +26,18 @@ int rvq_tc_workspace_bytes(int d, int num_sms, size_t* out);
 int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d, int nq,
                   int K, int q_begin, const float* cb, const void* cb_op, int nq_total, const float* cb_norm,
                   const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
-                  float* stats_cnt, void* ws, size_t ws_bytes, float* dbg_scores, float* dbg_rowscale,
-                  cudaStream_t st);
+                  float* stats_cnt, void* ws, size_t ws_bytes, float* dbg_scores, float* dbg_rowscale, int cluster,
+                  unsigned long long* prof, cudaStream_t st);
+bool rvq_fr_supported(int d);
+int rvq_launch_fr(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d, int nq,
+                  int K, int q_begin, const float* cb, const void* cb_op, int nq_total, const float* cb_norm,
+                  const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
+                  float* stats_cnt, int cluster, unsigned long long* prof, cudaStream_t st);
 bool rvq_tr_supported(int d);
 int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d, int nq,
                   int K, int q_begin, const float* cb, const void* cb_op, int nq_total, const float* cb_norm,
                   const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
-                  float* stats_cnt, void* ws, size_t ws_bytes, cudaStream_t st);
+                  float* stats_cnt, int cluster, unsigned long long* prof, cudaStream_t st);
 int rvq_launch_exact_scan(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d,
                           int nq, int K, const float* cb, const float* meta, float* xq, long long* idx,
                           double* commit_sq, float* stats_sum, float* stats_cnt, cudaStream_t st);
@@ -101,7 +105,6 @@ extern "C" int rvq_encode(const float* x, long long N, long long L, long long st
     if (int e = require_sm100("rvq_encode")) return e;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RVQ_CUDA(cudaMemsetAsync(commit_sq, 0, sizeof(double) * nq_use, st));
-    if (N == 0) return RVQ_OK;
     const int algo = flags & RVQ_FLAG_ALGO_MASK;
     if (algo == RVQ_ALGO_EXACT_SCAN)
         return rvq_launch_exact_scan(x, N, L, stride_b, stride_l, stride_d, d, nq_use, K, cb, cb_meta, xq, idx,
@@ -114,14 +117,53 @@ extern "C" int rvq_encode(const float* x, long long N, long long L, long long st
         set_error("rvq_encode: cb_op is null");
         return RVQ_ERR_ARG;
     }
-    // d <= 128: residual resident in tensor memory (rvq_encode_tr.cu); RVQ_KERNEL=tc forces the generic kernel
-    static const bool force_tc = getenv("RVQ_KERNEL") && !strcmp(getenv("RVQ_KERNEL"), "tc");
-    if (rvq_tr_supported(d) && !force_tc)
-        return rvq_launch_tr(x, N, L, stride_b, stride_l, stride_d, d, nq_use, K, 0, cb, cb_op, nq_use, cb_norm, cb_meta,
-                             xq, idx, commit_sq, stats_sum, stats_cnt, ws, ws_bytes, st);
+    const int kernel = flags & RVQ_FLAG_KERNEL_MASK;
+    const int cluster = (flags & RVQ_FLAG_CLUSTER_MASK) >> RVQ_FLAG_CLUSTER_SHIFT;
+    if (cluster != 0 && cluster != 1 && cluster != 2 && cluster != 4) {
+        set_error("rvq_encode: cluster size must be 1, 2 or 4 (got %d)", cluster);
+        return RVQ_ERR_ARG;
+    }
+    unsigned long long* prof = nullptr;
+    if (flags & RVQ_FLAG_COUNTERS) {
+        if (!ws || ws_bytes < 256) {
+            set_error("rvq_encode: RVQ_FLAG_COUNTERS needs a workspace of at least 256 bytes");
+            return RVQ_ERR_WORKSPACE;
+        }
+        // 32 counters live in the LAST 256 bytes of the workspace
+        prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 256) & ~(size_t)7));
+        RVQ_CUDA(cudaMemsetAsync(prof, 0, 256, st));
+    }
+    switch (kernel) {
+        case RVQ_KERNEL_AUTO:
+            // the fastest measured kernel per feature dimension (profiles/): d = 64 / 128 the
+            // TMEM-resident kernel with separate scan and update warps, larger d the generic kernel
+            if (rvq_tr_supported(d))
+                return rvq_launch_tr(x, N, L, stride_b, stride_l, stride_d, d, nq_use, K, 0, cb, cb_op, nq_use, cb_norm,
+                                     cb_meta, xq, idx, commit_sq, stats_sum, stats_cnt, cluster, prof, st);
+            break;
+        case RVQ_KERNEL_TMEM:
+            if (!rvq_tr_supported(d)) {
+                set_error("rvq_encode: RVQ_KERNEL_TMEM supports d = 64, 128 (got %d)", d);
+                return RVQ_ERR_ARG;
+            }
+            return rvq_launch_tr(x, N, L, stride_b, stride_l, stride_d, d, nq_use, K, 0, cb, cb_op, nq_use, cb_norm,
+                                 cb_meta, xq, idx, commit_sq, stats_sum, stats_cnt, cluster, prof, st);
+        case RVQ_KERNEL_FRAME:
+            if (!rvq_fr_supported(d)) {
+                set_error("rvq_encode: RVQ_KERNEL_FRAME supports d = 64, 128, 256 (got %d)", d);
+                return RVQ_ERR_ARG;
+            }
+            return rvq_launch_fr(x, N, L, stride_b, stride_l, stride_d, d, nq_use, K, 0, cb, cb_op, nq_use, cb_norm,
+                                 cb_meta, xq, idx, commit_sq, stats_sum, stats_cnt, cluster, prof, st);
+        case RVQ_KERNEL_GENERIC:
+            break;
+        default:
+            set_error("rvq_encode: unknown kernel selector 0x%x", kernel);
+            return RVQ_ERR_ARG;
+    }
     // the TMA descriptor spans stages [0, nq_use): later stages are never addressed
     return rvq_launch_tc(x, N, L, stride_b, stride_l, stride_d, d, nq_use, K, 0, cb, cb_op, nq_use, cb_norm, cb_meta,
-                         xq, idx, commit_sq, stats_sum, stats_cnt, ws, ws_bytes, nullptr, nullptr, st);
+                         xq, idx, commit_sq, stats_sum, stats_cnt, ws, ws_bytes, nullptr, nullptr, cluster, prof, st);
 }
 
 extern "C" int rvq_debug_stage_scores(const float* x, int d, int K, int stage, const void* cb_op, const float* cb_norm,
@@ -151,7 +193,7 @@ extern "C" int rvq_debug_stage_scores(const float* x, int d, int K, int stage, c
     void* ws = b + n_xq * 4 + TILE_M * 8 + 64;
     float* fake_cb = reinterpret_cast<float*>(b + n_xq * 4 + TILE_M * 8 + 64 + ws_bytes);  // zeros: gather is harmless
     int rc = rvq_launch_tc(x, TILE_M, TILE_M, 0, d, 1, d, 1, K, stage, fake_cb, cb_op, stage + 1, cb_norm, cb_meta, xq,
-                           idx, csq, nullptr, nullptr, ws, ws_bytes, scores, row_scale, st);
+                           idx, csq, nullptr, nullptr, ws, ws_bytes, scores, row_scale, 1, nullptr, st);
     cudaFreeAsync(tmp, st);
     return rc;
 }

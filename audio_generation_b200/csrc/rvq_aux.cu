@@ -197,9 +197,9 @@ __global__ void dequantize_rows(const float* __restrict__ cb, const long long* _
             *reinterpret_cast<float4*>(o + i) = acc;
         }
     } else {
+        // launched with ceil(N / 128) * 128 * d threads: the last group of 128 frames is padded, so the guard is on
+        // the frame number only (a guard on t < N * d dropped features of the last group when N % 128 != 0)
         const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        const long long total = N * d;
-        if (t >= total) return;
         const long long chunk = 128;  // frames-fastest inside groups of 128 frames
         const long long g = t / (chunk * d), rem = t % (chunk * d);
         const int i = (int)(rem / chunk);
@@ -331,6 +331,22 @@ extern "C" int rvq_ema_finalize(float* cb, float* ema_count, float* ema_sum, con
     const int block = 256;
     k3_codes<<<(unsigned)((warps * 32 + block - 1) / block), block, 0, st>>>(cb, ema_count, ema_sum, stats_sum, k_valid,
                                                                              ntot, nq_use, K, d, decay, omd, eps);
+    RVQ_CUDA(cudaGetLastError());
+    RVQ_CUDA(cudaFreeAsync(ntot, st));
+    return RVQ_OK;
+}
+
+extern "C" int rvq_ema_counts(float* ema_count, const float* stats_cnt, const int* k_valid, int nq_use, int K,
+                              float decay, void* stream) {
+    if (nq_use <= 0 || K <= 0 || !ema_count || !stats_cnt) {
+        set_error("rvq_ema_counts: bad argument");
+        return RVQ_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* ntot = nullptr;
+    RVQ_CUDA(cudaMallocAsync(&ntot, sizeof(float) * nq_use, st));
+    const float omd = (float)(1.0 - (double)decay);
+    k3_counts<<<nq_use, 1024, 0, st>>>(ema_count, stats_cnt, k_valid, K, decay, omd, ntot);
     RVQ_CUDA(cudaGetLastError());
     RVQ_CUDA(cudaFreeAsync(ntot, st));
     return RVQ_OK;

@@ -18,7 +18,6 @@
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4-7 / 8-11 = epilogue groups 0 / 1 (accumulator buffers 0 / 1).
 #include <cuda.h>
-#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -878,8 +877,8 @@ int rvq_tc_workspace_bytes(int d, int num_sms, size_t* out) {
 int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d, int nq,
                   int K, int q_begin, const float* cb, const void* cb_op, int nq_total, const float* cb_norm,
                   const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
-                  float* stats_cnt, void* ws, size_t ws_bytes, float* dbg_scores, float* dbg_rowscale,
-                  cudaStream_t st) {
+                  float* stats_cnt, void* ws, size_t ws_bytes, float* dbg_scores, float* dbg_rowscale, int cluster,
+                  unsigned long long* prof, cudaStream_t st) {
     if (K > 32 * CHUNK_N) {
         set_error("rvq_encode: at most %d codes per stage are supported (got %d)", 32 * CHUNK_N, K);
         return RVQ_ERR_ARG;
@@ -906,10 +905,9 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nq_total * Kpad};
     const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
-    // Codebook multicast across a cluster is available here too (RVQ_CLUSTER_TC=2|4) but measured slower for
+    // Codebook multicast across a cluster is available here too (cluster = 2 | 4) but measured slower for
     // this kernel (C4 shape: 5.5 -> 3.1 M frames/s: a slow exact scan in one CTA stalls its whole cluster).
-    static const int cluster_env = getenv("RVQ_CLUSTER_TC") ? atoi(getenv("RVQ_CLUSTER_TC")) : 1;
-    const int CL = dbg_scores ? 1 : ((cluster_env == 1 || cluster_env == 2 || cluster_env == 4) ? cluster_env : 1);
+    const int CL = dbg_scores ? 1 : ((cluster == 2 || cluster == 4) ? cluster : 1);
     const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)(CHUNK_N / CL)};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(cb_op), gdim, gstride, box,
@@ -949,12 +947,7 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     p.off_misc = sp.off_misc;
     p.dbg_scores = dbg_scores;
     p.dbg_rowscale = dbg_rowscale;
-    static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
-    if (want_prof && ws && ws_bytes >= 256) {
-        // 32 counters live in the LAST 256 bytes of the workspace
-        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 256) & ~(size_t)7));
-        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 256, st));
-    }
+    p.prof = prof;  // 32 counters (RVQ_FLAG_COUNTERS) or null
     {
         const size_t need = (size_t)grid * 2 * TILE_M * d * sizeof(float);
         uintptr_t base = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;

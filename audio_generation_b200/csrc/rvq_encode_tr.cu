@@ -19,7 +19,6 @@
 // warps 4-7 / 8-11 = scan groups 0 / 1 (accumulator buffers 0 / 1), warps 12-15 / 16-19 = update groups of
 // tile slots 0 / 1 (thread = frame).
 #include <cuda.h>
-#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -82,9 +81,7 @@ struct __align__(16) Misc {
     uint32_t g_rows[2][2][2][TILE_M];  // [slot][stage parity][group][frame]: loads that may hold a candidate
     uint16_t g_cols[2][2][2][TILE_M];  // [slot][stage parity][group][frame]: columns that may hold a candidate
     int win[2][TILE_M];             // [slot][frame]: selected code
-    int n_special[2], n_dirty[2], n_srows[2], n_hard[2];
-    uint8_t pos_of[2][TILE_M];   // [slot][frame]: its row in the verification buffer
-    uint8_t repair[2][TILE_M];   // [slot][frame]: the last stage's winner was corrected after the operand went out
+    int n_special[2], n_dirty[2];
     uint32_t pairs[2][RS_ROWS * 4];      // [slot][entry * 4 + t]: code scored
     float pair_score[2][RS_ROWS * 4];    // its exact score
     uint16_t special_rows[2][4 * TILE_M];  // [slot][entry]: frame | block << 8 | 0x8000 if it needs the exact scan
@@ -93,13 +90,10 @@ struct __align__(16) Misc {
     double commit_acc[MAX_NQ];
 };
 
-#include "tr_update_spec.cuh"
 
 // kStats: EMA statistics requested (compile-time so that each instantiation carries one apply path only: the
 // update threads are register-bound)
-// kSpec (only without statistics): speculative update with exact verification behind the next stage
-// (tr_update_spec.cuh; RVQ_SPEC=1).  Bit-identical results; measured slower on C2, kept selectable.
-template <bool kStats, bool kSpec>
+template <bool kStats>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -134,8 +128,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             mbar_init(&misc->stg_full[i], GRP_THREADS);
             misc->n_special[i] = 0;
             misc->n_dirty[i] = 0;
-            misc->n_srows[i] = 0;
-            misc->n_hard[i] = 0;
         }
         mbar_init(&misc->stg_free, GRP_THREADS);
         for (int i = 0; i < MAX_NQ; ++i) misc->commit_acc[i] = 0.0;
@@ -338,10 +330,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
         const int s = (warp - UPD_WARP0) >> 2;    // tile slot served by this group
         const int row = (warp & 3) * 32 + lane;   // frame of the tile = TMEM lane (UPD_WARP0 % 4 == 0)
         const int gw = warp & 3;                  // warp inside the group
-        if constexpr (kSpec) {
-            // speculative update, exact verification behind the next stage (tr_update_spec.cuh)
-            update_group_spec(p, misc, smem, staging, tmem_base, warp, lane, n_local);
-        } else if (s < nslots) {
+        if (s < nslots) {
             const uint32_t t_r = tmem_base + ((uint32_t)(gw * 32) << 16) + TMEM_RES_COL + (uint32_t)(s * d);
             float* stg_row = staging + (size_t)row * p.pitch;
             float* stg_warp = staging + (size_t)(gw * 32) * p.pitch;  // first staging row of this warp's frames
@@ -944,7 +933,7 @@ bool rvq_tr_supported(int d) { return d == 64 || d == 128; }
 int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long long sl, long long sd, int d, int nq,
                   int K, int q_begin, const float* cb, const void* cb_op, int nq_total, const float* cb_norm,
                   const float* cb_meta, float* xq, long long* idx, double* commit_sq, float* stats_sum,
-                  float* stats_cnt, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  float* stats_cnt, int cluster, unsigned long long* prof, cudaStream_t st) {
     if (K > 32 * CHUNK_N) {
         set_error("rvq_encode: at most %d codes per stage are supported (got %d)", 32 * CHUNK_N, K);
         return RVQ_ERR_ARG;
@@ -962,10 +951,7 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     p.nslots = 2;
     p.pitch = d + 4;
     const uint32_t a_bytes = (uint32_t)(d / KSLICE) * A_SLICE_BYTES;
-    static const bool spec_env = getenv("RVQ_SPEC") && atoi(getenv("RVQ_SPEC")) != 0;
-    const bool spec = spec_env && !stats_sum;
-    // staging buffer of one tile, or (speculative update) the verification row buffers of the two slots
-    const int stg_rows = spec ? 2 * tr::RS_CAP : TILE_M;
+    const int stg_rows = TILE_M;  // staging buffer of one tile
     const uint32_t stg_bytes = (uint32_t)((stg_rows * p.pitch * 4 + 1023) / 1024 * 1024);
     const uint32_t misc_bytes = (uint32_t)((sizeof(tr::Misc) + 1023) / 1024 * 1024);
     p.off_stg = (uint32_t)p.nslots * a_bytes;
@@ -989,8 +975,7 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nq_total * Kpad};
     const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
-    static const int cluster_env = getenv("RVQ_CLUSTER") ? atoi(getenv("RVQ_CLUSTER")) : 2;
-    const int CL = (cluster_env == 1 || cluster_env == 2 || cluster_env == 4) ? cluster_env : 2;
+    const int CL = (cluster == 1 || cluster == 2 || cluster == 4) ? cluster : 2;
     p.cluster = CL;
     const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)(tr::CH / CL)};
     const cuuint32_t estr[2] = {1, 1};
@@ -1019,14 +1004,8 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     p.stats_sum = stats_sum;
     p.stats_cnt = stats_cnt;
     p.num_tiles = num_tiles;
-    static const bool want_prof = getenv("RVQ_PROFILE") != nullptr;
-    if (want_prof && ws && ws_bytes >= 256) {
-        // 32 counters live in the LAST 256 bytes of the workspace
-        p.prof = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(ws) + ((ws_bytes - 256) & ~(size_t)7));
-        RVQ_CUDA(cudaMemsetAsync(p.prof, 0, 256, st));
-    }
-    auto kern = stats_sum ? tr::rvq_encode_tr_kernel<true, false>
-                          : (spec ? tr::rvq_encode_tr_kernel<false, true> : tr::rvq_encode_tr_kernel<false, false>);
+    p.prof = prof;  // 32 counters (RVQ_FLAG_COUNTERS) or null
+    auto kern = stats_sum ? tr::rvq_encode_tr_kernel<true> : tr::rvq_encode_tr_kernel<false>;
     RVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(tr::NUM_THREADS, 1, 1);

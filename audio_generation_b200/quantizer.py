@@ -21,7 +21,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._lib import RVQError, RVQ_ALGO_EXACT_SCAN, RVQ_ALGO_TENSOR
+from ._lib import (RVQError, RVQ_ALGO_EXACT_SCAN, RVQ_ALGO_TENSOR, RVQ_FLAG_CLUSTER_SHIFT, RVQ_FLAG_COUNTERS,
+                   RVQ_KERNELS)
 
 EMA_DECAY = 0.99   # ASSUMED (rosinality / Jukebox lineage, README.md:26-27)
 EMA_EPS = 1e-5     # ASSUMED
@@ -154,7 +155,7 @@ class ResidualQuantizer(nn.Module):
     def __init__(self, num_quantizers, dim, quantizer_class="ema", codebook_sizes=1024,
                  vq_cutoff_freq=1, use_som=True, som_kernel_type="hard",
                  decay=EMA_DECAY, eps=EMA_EPS, commitment_weight=1.0, algo="tensor",
-                 som_shrink=SOM_SHRINK, reseed_seed=0):
+                 som_shrink=SOM_SHRINK, reseed_seed=0, kernel="auto", cluster=0):
         super().__init__()
         if quantizer_class not in ("ema", "base"):
             raise ValueError(f"quantizer_class must be 'ema' or 'base', got {quantizer_class!r}")
@@ -170,6 +171,8 @@ class ResidualQuantizer(nn.Module):
         self.som_shrink, self.reseed_seed = float(som_shrink), int(reseed_seed)
         self.decay, self.eps, self.commitment_weight = float(decay), float(eps), float(commitment_weight)
         self.algo = algo
+        # launch options of the fused kernel (tests cross-check the kernels against each other; "auto" is the product)
+        self.kernel, self.cluster, self.counters = kernel, int(cluster), False
         K = max(self.codebook_sizes)
         self.K = K
         cb = torch.randn(self.num_quantizers, K, self.dim)   # ASSUMED init
@@ -320,6 +323,9 @@ class ResidualQuantizer(nn.Module):
             flat, ssum, scnt, rep = self._stats_buffers(dev)
             flat[: ssum.numel() + scnt.numel()].zero_()
         flags = RVQ_ALGO_EXACT_SCAN if self.algo == "exact_scan" else RVQ_ALGO_TENSOR
+        flags |= RVQ_KERNELS[self.kernel] | (self.cluster << RVQ_FLAG_CLUSTER_SHIFT)
+        if self.counters:
+            flags |= RVQ_FLAG_COUNTERS
         with torch.cuda.device(dev):
             if self.kernel_events is not None:
                 k0 = torch.cuda.Event(enable_timing=True)
@@ -335,6 +341,15 @@ class ResidualQuantizer(nn.Module):
                 self._update_codebooks(x3, N, L, sb, sl, sd, nq, idx, flat, ssum, scnt, rep)
         xq = xq.reshape(x.shape) if xq.shape != x.shape else xq
         return xq, idx.reshape(*x.shape[:-1], nq), commit_sq
+
+    def read_counters(self) -> List[int]:
+        """The 32 event counters of the last launch made with ``self.counters = True`` (last 256 bytes of the
+        workspace; synchronises)."""
+        ws = self._ws
+        if ws is None:
+            return [0] * 32
+        off = (ws.numel() - 256) & ~7
+        return ws[off: off + 256].view(torch.int64).cpu().tolist()
 
     def _backward(self, x, idx, cb, nq, g_out, g_commit, need_x, need_cb):
         """rvq_backward: gx = g_out + g_commit * w * 2/(N d) * sum_q r_{q+1}; gcb[q, idx] -= g_commit * 2/(N d) * r_{q+1}."""

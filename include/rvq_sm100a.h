@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RVQ_ABI_VERSION 6
+#define RVQ_ABI_VERSION 7
 
 typedef enum {
     RVQ_OK = 0,
@@ -39,6 +39,18 @@ typedef enum {
 #define RVQ_ALGO_TENSOR 0      /* tcgen05 fp16 filter + exact fp32 re-rank (product path)       */
 #define RVQ_ALGO_EXACT_SCAN 1  /* exact fp32 CUDA-core scan of every code (verification, tiny N) */
 #define RVQ_FLAG_ALGO_MASK 0xF
+/* kernel choice of RVQ_ALGO_TENSOR (bits 4-7).  All kernels share one exact scorer and return bit-identical
+ * codes; AUTO is the product path (the fastest measured kernel per d), the others let tests cross-check it. */
+#define RVQ_KERNEL_AUTO 0x00     /* TMEM kernel for d = 64 / 128, generic kernel otherwise                          */
+#define RVQ_KERNEL_GENERIC 0x10  /* rvq_encode_tc.cu: residual in an L2-resident scratch, any d                     */
+#define RVQ_KERNEL_FRAME 0x20    /* rvq_encode_fr.cu: thread = frame, residual in tensor memory, d = 64 / 128 / 256 */
+#define RVQ_KERNEL_TMEM 0x30     /* rvq_encode_tr.cu: residual in tensor memory, scan and update warps, d = 64 / 128 */
+#define RVQ_FLAG_KERNEL_MASK 0xF0
+/* CTAs per cluster sharing one multicast codebook stream (bits 8-10): 0 = the kernel's default, else 1, 2 or 4 */
+#define RVQ_FLAG_CLUSTER_SHIFT 8
+#define RVQ_FLAG_CLUSTER_MASK 0x700
+/* event counters of the launch in the LAST 256 bytes of ws (uint64[32], zeroed by the call): test / profiling aid */
+#define RVQ_FLAG_COUNTERS 0x1000
 
 int rvq_version(void);
 const char* rvq_last_error(void);
@@ -78,7 +90,7 @@ int rvq_workspace_bytes(int nq, int K, int d, long long N, size_t* out);
  *   stats_sum  fp32 [nq_total, K, d] nullable, stats_cnt fp32 [nq_total, K] nullable: EMA statistics,
  *              ACCUMULATED into (caller zeroes): cnt[q,k] += #{n: idx=k}, sum[q,k,:] += r_q[n,:]
  *   ws / ws_bytes   scratch of at least rvq_workspace_bytes
- *   flags    RVQ_ALGO_*                                                                          */
+ *   flags    RVQ_ALGO_* | RVQ_KERNEL_* | cluster size << RVQ_FLAG_CLUSTER_SHIFT | RVQ_FLAG_COUNTERS      */
 int rvq_encode(const float* x, long long N, long long L, long long stride_b, long long stride_l,
                long long stride_d, int d, int nq_use, int K,
                const float* cb, const void* cb_op, const float* cb_norm, const float* cb_meta,
@@ -93,6 +105,12 @@ int rvq_encode(const float* x, long long N, long long L, long long stride_b, lon
 int rvq_ema_finalize(float* cb, float* ema_count, float* ema_sum,
                      const float* stats_sum, const float* stats_cnt, const int* k_valid,
                      int nq_use, int K, int d, float decay, float eps, void* stream);
+
+/* The count half of K3 alone: ema_count = decay*ema_count + (1-decay)*cnt over stages 0..nq_use-1.  For
+ * quantizer_class "base" (/root/reference/config/training.yml:21), whose codebooks are trained by gradient: the
+ * usage statistics still feed get_stale_clusters() / the stale-code re-seeding (training.py:435,461). */
+int rvq_ema_counts(float* ema_count, const float* stats_cnt, const int* k_valid, int nq_use, int K, float decay,
+                   void* stream);
 
 /* Code lookup (ResidualQuantizer.quantizers[i].dequantize, /root/reference/networks/vae.py:333,
  * summed over stages as CausalVQAE.sample does at vae.py:329-334):

@@ -1,14 +1,13 @@
-"""GPU tests (-m gpu) of the two fused encode kernels and their launch variants.
+"""GPU tests (-m gpu) of the fused encode kernels and their launch variants.
 
-d <= 128 runs `rvq_encode_tr_kernel` (residual resident in tensor memory, norm term folded into the MMA, cluster
-multicast of the codebook stream); other d, or RVQ_KERNEL=tc, runs the generic `rvq_encode_tc_kernel`.  Both use the
-same exact fp32 scorer for every frame the fp16 filter cannot certify, so on the same input they must return
-bit-identical code indices and outputs, whatever the cluster size - and whether the update waits for the exact
-re-rank or speculates on the approximate argmin and verifies / repairs afterwards (RVQ_SPEC=1).  The environment
-switches are read once per process, hence the subprocesses.
+d = 64 / 128 / 256 runs `rvq_encode_fr_kernel` (thread = frame, residual resident in tensor memory, norm term folded
+into the MMA, cluster multicast of the codebook stream); other d, or kernel="generic", runs `rvq_encode_tc_kernel`;
+kernel="tmem" is round 1's kernel for d <= 128 (separate scan and update warps).  All of them use the same exact
+fp32 scorer for every frame the fp16 filter cannot certify, so on the same input they must return bit-identical code
+indices and outputs, whatever the cluster size.  The variants are selected through `flags` bits of `rvq_encode`
+(include/rvq_sm100a.h), not through the environment.
 """
 import os
-import subprocess
 import sys
 
 import pytest
@@ -17,60 +16,52 @@ import torch
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-WORKER = r"""
-import sys, torch
-sys.path.insert(0, {root!r})
-from audio_generation_b200 import ResidualQuantizer
-nq, K, d, N, strided, update = {nq}, {K}, {d}, {N}, {strided}, {update}
-torch.manual_seed(3)
-m = ResidualQuantizer(nq, d, "ema", K)
-with torch.no_grad():
-    for q in range(nq):
-        m.codebooks[q].mul_(0.7 ** q)
-    m.ema_sum.copy_(m.codebooks)
-m = m.cuda()
-g = torch.Generator(device="cuda").manual_seed(5)
-if strided:
-    L = 125
-    x = torch.randn(N // L, d, L, device="cuda", generator=g).permute(0, 2, 1)   # (B, L, d) view of (B, d, L)
-else:
-    x = torch.randn(N, d, device="cuda", generator=g)
-m.train(update)
-with torch.no_grad():
-    xq, idx, commit = m(x, None, update_codebook=update)
-torch.cuda.synchronize()
-torch.save(dict(idx=idx.cpu(), xq=xq.contiguous().cpu(), commit=float(commit), cb=m.codebooks.cpu(),
-                cnt=m.ema_count.cpu()), {out!r})
-"""
+
+def run_variant(kernel, cluster, nq, K, d, N, strided, update):
+    from audio_generation_b200 import ResidualQuantizer
+    torch.manual_seed(3)
+    m = ResidualQuantizer(nq, d, "ema", K, kernel=kernel, cluster=cluster)
+    with torch.no_grad():
+        for q in range(nq):
+            m.codebooks[q].mul_(0.7 ** q)
+        m.ema_sum.copy_(m.codebooks)
+    m = m.cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    if strided:
+        L = 125
+        x = torch.randn(N // L, d, L, device="cuda", generator=g).permute(0, 2, 1)   # (B, L, d) view of (B, d, L)
+    else:
+        x = torch.randn(N, d, device="cuda", generator=g)
+    m.train(update)
+    with torch.no_grad():
+        xq, idx, commit = m(x, None, update_codebook=update)
+    torch.cuda.synchronize()
+    return dict(idx=idx.cpu(), xq=xq.contiguous().cpu(), commit=float(commit), cb=m.codebooks.cpu(),
+                cnt=m.ema_count.cpu())
 
 
-def run_variant(tmp_path, name, env, **kw):
-    out = str(tmp_path / f"{name}.pt")
-    code = WORKER.format(root=ROOT, out=out, **kw)
-    e = dict(os.environ)
-    e.update(env)
-    r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
-    return torch.load(out)
-
-
-@pytest.mark.parametrize("d,K,N,strided", [(128, 1024, 20000, False), (64, 300, 5000, False), (128, 512, 8000, True)])
-def test_tmem_resident_kernel_equals_generic_kernel(tmp_path, d, K, N, strided):
+@pytest.mark.parametrize("d,K,N,strided", [(128, 1024, 20000, False), (64, 300, 5000, False), (128, 512, 8000, True),
+                                           (256, 1024, 12000, False), (256, 512, 6000, True)])
+def test_kernels_agree_bitwise(d, K, N, strided):
     kw = dict(nq=5, K=K, d=d, N=N, strided=strided, update=False)
-    a = run_variant(tmp_path, "tr2", {"RVQ_CLUSTER": "2"}, **kw)
-    for name, env in [("tr1", {"RVQ_CLUSTER": "1"}), ("tr4", {"RVQ_CLUSTER": "4"}), ("spec", {"RVQ_SPEC": "1"}),
-                      ("tc", {"RVQ_KERNEL": "tc"}), ("tc2", {"RVQ_KERNEL": "tc", "RVQ_CLUSTER_TC": "2"})]:
-        b = run_variant(tmp_path, name, env, **kw)
+    a = run_variant("frame", 2, **kw)
+    variants = [("frame", 1), ("frame", 4), ("generic", 0), ("generic", 2)]
+    if d <= 128:
+        variants += [("tmem", 1), ("tmem", 2)]
+    for kernel, cluster in variants:
+        b = run_variant(kernel, cluster, **kw)
+        name = f"{kernel}/{cluster}"
         assert torch.equal(a["idx"], b["idx"]), name
         assert torch.equal(a["xq"], b["xq"]), name
         assert abs(a["commit"] - b["commit"]) <= 1e-6 * abs(a["commit"]), name
 
 
-def test_statistics_variants_agree(tmp_path):
-    """EMA statistics: bulk reductions (tr kernel) vs vector atomics (generic kernel) give the same update."""
-    kw = dict(nq=3, K=512, d=128, N=30000, strided=False, update=True)
-    a = run_variant(tmp_path, "tr", {}, **kw)
-    b = run_variant(tmp_path, "tc", {"RVQ_KERNEL": "tc"}, **kw)
+@pytest.mark.parametrize("d", [128, 256])
+def test_statistics_variants_agree(d):
+    """EMA statistics: the frame-resident kernel and the generic kernel give the same update."""
+    kw = dict(nq=3, K=512, d=d, N=30000, strided=False, update=True)
+    a = run_variant("frame", 0, **kw)
+    b = run_variant("generic", 0, **kw)
     assert torch.equal(a["idx"], b["idx"])
     assert torch.allclose(a["cnt"], b["cnt"], rtol=0, atol=0)
     assert torch.allclose(a["cb"], b["cb"], rtol=1e-5, atol=1e-6)

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.rvq_version() == 6
+    assert lib.rvq_version() == _lib.RVQ_ABI_VERSION == 7
 
 
 def test_argument_checks_need_no_gpu():
