@@ -82,7 +82,9 @@ def _frame_addressing(x: torch.Tensor):
     if ok and x3.stride(2) == 1:
         ok = (x3.stride(1) % 4 == 0) and (x3.stride(0) % 4 == 0) and (x3.data_ptr() % 16 == 0)
     if not ok:
-        x3 = x3.contiguous()
+        # .contiguous() is a no-op on a tensor that already is contiguous but sits at an unaligned offset (a view into
+        # a larger buffer) or whose strides of size-1 dimensions are arbitrary: force a fresh, aligned copy
+        x3 = x3.clone(memory_format=torch.contiguous_format)
     B, L, _ = x3.shape
     return x3, B * L, L, x3.stride(0), x3.stride(1), x3.stride(2)
 
@@ -122,12 +124,18 @@ class _RVQFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, codebooks, mod, nq, update):
-        xq, idx, commit_sq = mod._encode(x, nq, update)
+        # With update=True the codebook maintenance (EMA refresh, stale-code re-seeding) rewrites `codebooks` through
+        # raw pointers right after the encode: autograd cannot see that write, and backward re-walks the residual
+        # chain r_{q+1} = r_q - C_q[idx].  So the codebooks the indices were computed with are snapshotted first.
+        # SOM width of THIS call (the update below increments the step counter)
+        som_t = mod._update_step_index() if (mod.use_som and mod.quantizer_class == "base") else None
+        xq, idx, commit_sq, cb_used = mod._encode(x, nq, update, snapshot=update)
         N = idx.numel() // nq
         w = mod.commitment_weight + (1.0 if mod.quantizer_class == "base" else 0.0)
         commit = (commit_sq.sum() * (w / max(N * mod.dim, 1))).to(torch.float32)
         ctx.mod, ctx.nq = mod, nq
-        ctx.save_for_backward(x, idx, codebooks)
+        ctx.som_t = som_t
+        ctx.save_for_backward(x, idx, codebooks if cb_used is None else cb_used)
         ctx.mark_non_differentiable(idx)
         out = x + (xq - x)
         return out, idx, commit
@@ -140,7 +148,8 @@ class _RVQFunction(torch.autograd.Function):
         need_cb = ctx.needs_input_grad[1] and mod.quantizer_class == "base"
         if g_commit is None or not (need_x or need_cb):
             return (g_out if need_x else None), None, None, None, None
-        gx, gcb = mod._backward(x, idx, codebooks.detach(), nq, g_out if need_x else None, g_commit, need_x, need_cb)
+        gx, gcb = mod._backward(x, idx, codebooks.detach(), nq, g_out if need_x else None, g_commit, need_x, need_cb,
+                                som_t=ctx.som_t)
         return gx, gcb, None, None, None
 
 
@@ -195,6 +204,8 @@ class ResidualQuantizer(nn.Module):
         self._spread = None
         self.last_stats = None     # flat [sum | cnt | replacement vectors] of the most recent update (for inspection)
         self.kernel_events = None  # a list collects (start, stop) CUDA events around every rvq_encode launch (bench.py)
+        self.comm_events = None    # ... and around every all-reduce of the statistics
+        self.sync_stats = True     # False: every rank updates from its own shard only (replicas DIVERGE; measurements)
 
     # ------------------------------------------------------------------ derived operands / scratch
     def _apply(self, fn, *a, **k):
@@ -256,17 +267,23 @@ class ResidualQuantizer(nn.Module):
 
     def _update_codebooks(self, x3, N, L, sb, sl, sd, nq, idx, flat, ssum, scnt, rep):
         """All-reduce of the statistics -> SOM neighbourhood -> EMA refresh -> stale-code re-seeding (K3 and
-        SURVEY 8f rows 2, 3), on the current stream."""
+        SURVEY 8f rows 2, 3), on the current stream.
+
+        quantizer_class "base" (the reference's config/training.yml:21 passes update_codebook=True for it too,
+        training.py:305-308): the codebooks are trained by gradient, so only the usage counts are averaged
+        (get_stale_clusters / update_cutoff stay meaningful, training.py:435,454,461) and stale codes are re-seeded;
+        the SOM neighbourhood acts on the codebook gradient instead (``_backward``).  ASSUMED semantics."""
         lib = _lib.load()
         K, d = self.K, self.dim
+        ema = self.quantizer_class == "ema"
         cb = self.codebooks.detach()
         dist = torch.distributed
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() and self.sync_stats else 1
         rank = dist.get_rank() if world > 1 else 0
         t = self._update_step_index()
         cutoff = self.vq_cutoff_freq
         reseed = cutoff > 0
-        payload = flat
+        nsum, ncnt = self.num_quantizers * K * d, self.num_quantizers * K
         if reseed:
             # replacement vectors need the codebooks `idx` was computed with: gathered BEFORE the EMA refresh; frames
             # are numbered globally (equal shards per rank), non-owners contribute zeros to the sum
@@ -274,36 +291,50 @@ class ResidualQuantizer(nn.Module):
             _lib.check(lib.rvq_reseed_gather(_ptr(x3), N, L, sb, sl, sd, d, nq, K, _ptr(cb), _ptr(idx),
                                              _ptr(self.ema_count), self.decay, cutoff, seed, rank * N, N * world,
                                              _ptr(rep), _stream()), "rvq_reseed_gather")
-        else:
-            payload = flat[: self.num_quantizers * K * (d + 1)]
+        # one flat payload [sum | cnt | rep]: "ema" sends [sum | cnt (| rep)], "base" only [cnt (| rep)]
+        lo = 0 if ema else nsum
+        hi = nsum + ncnt + (nsum if reseed else 0)
         if world > 1:
-            # the only place the path crosses frame shards: one SUM all-reduce of [sum | cnt | rep]
-            dist.all_reduce(payload, op=dist.ReduceOp.SUM)
-        if self.use_som:
-            radius, w = som_weights(self.som_kernel_type, t, self.som_shrink)
-            hw = []
-            for q in range(nq):
-                hw += list(approximate_square_root(self.codebook_sizes[q]))
-            nsum = self.num_quantizers * K * d
-            ssum2, scnt2 = self._spread[:nsum], self._spread[nsum:]
-            _lib.check(lib.rvq_som_spread(_ptr(ssum), _ptr(scnt), _ptr(ssum2), _ptr(scnt2), (C.c_int * len(hw))(*hw),
-                                          nq, K, d, radius, (C.c_float * len(w))(*w), _stream()), "rvq_som_spread")
-            ssum, scnt = ssum2, scnt2
-        _lib.check(lib.rvq_ema_finalize(_ptr(cb), _ptr(self.ema_count), _ptr(self.ema_sum), _ptr(ssum), _ptr(scnt),
-                                        _ptr(self.k_valid), nq, K, d, self.decay, self.eps, _stream()),
-                   "rvq_ema_finalize")
+            # the only place the path crosses frame shards: one SUM all-reduce
+            if self.comm_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM)
+            if self.comm_events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.comm_events.append((e0, e1))
+        if ema:
+            if self.use_som:
+                radius, w = som_weights(self.som_kernel_type, t, self.som_shrink)
+                hw = []
+                for q in range(nq):
+                    hw += list(approximate_square_root(self.codebook_sizes[q]))
+                ssum2, scnt2 = self._spread[:nsum], self._spread[nsum:]
+                _lib.check(lib.rvq_som_spread(_ptr(ssum), _ptr(scnt), _ptr(ssum2), _ptr(scnt2), (C.c_int * len(hw))(*hw),
+                                              nq, K, d, radius, (C.c_float * len(w))(*w), _stream()), "rvq_som_spread")
+                ssum, scnt = ssum2, scnt2
+            _lib.check(lib.rvq_ema_finalize(_ptr(cb), _ptr(self.ema_count), _ptr(self.ema_sum), _ptr(ssum), _ptr(scnt),
+                                            _ptr(self.k_valid), nq, K, d, self.decay, self.eps, _stream()),
+                       "rvq_ema_finalize")
+        else:
+            _lib.check(lib.rvq_ema_counts(_ptr(self.ema_count), _ptr(scnt), _ptr(self.k_valid), nq, K, self.decay,
+                                          _stream()), "rvq_ema_counts")
         if reseed:
             _lib.check(lib.rvq_reseed_apply(_ptr(cb), _ptr(self.ema_count), _ptr(self.ema_sum), _ptr(rep),
                                             _ptr(self.k_valid), nq, K, d, cutoff, cutoff, _ptr(self.n_replaced),
                                             _stream()), "rvq_reseed_apply")
         self.update_steps += 1
         self._steps_host = t + 1
-        self._derived = None     # codebooks changed: operands are rebuilt before the next call
+        if ema or reseed:
+            self._derived = None     # codebooks changed: operands are rebuilt before the next call
         self.last_stats = flat
 
     # ------------------------------------------------------------------ the hot path
-    def _encode(self, x: torch.Tensor, nq: int, update: bool, ws: Optional[torch.Tensor] = None):
-        """Run K1(+K2) [+ all-reduce + K3] on ``x`` (..., L, d); returns (xq like x, idx (..., L, nq), commit_sq)."""
+    def _encode(self, x: torch.Tensor, nq: int, update: bool, ws: Optional[torch.Tensor] = None,
+                snapshot: bool = False):
+        """Run K1(+K2) [+ all-reduce + K3] on ``x`` (..., L, d); returns (xq like x, idx (..., L, nq), commit_sq,
+        copy of the codebooks the indices refer to if ``snapshot`` and the call updated them, else None)."""
         lib = _lib.load()
         self._check_device(x)
         if x.dtype != torch.float32:
@@ -337,10 +368,14 @@ class ResidualQuantizer(nn.Module):
                 k1 = torch.cuda.Event(enable_timing=True)
                 k1.record()
                 self.kernel_events.append((k0, k1))
+            cb_used = None
             if update:
+                if snapshot:
+                    cb_used = cb.clone()
+                self._update_step_index()
                 self._update_codebooks(x3, N, L, sb, sl, sd, nq, idx, flat, ssum, scnt, rep)
         xq = xq.reshape(x.shape) if xq.shape != x.shape else xq
-        return xq, idx.reshape(*x.shape[:-1], nq), commit_sq
+        return xq, idx.reshape(*x.shape[:-1], nq), commit_sq, cb_used
 
     def read_counters(self) -> List[int]:
         """The 32 event counters of the last launch made with ``self.counters = True`` (last 256 bytes of the
@@ -351,8 +386,10 @@ class ResidualQuantizer(nn.Module):
         off = (ws.numel() - 256) & ~7
         return ws[off: off + 256].view(torch.int64).cpu().tolist()
 
-    def _backward(self, x, idx, cb, nq, g_out, g_commit, need_x, need_cb):
-        """rvq_backward: gx = g_out + g_commit * w * 2/(N d) * sum_q r_{q+1}; gcb[q, idx] -= g_commit * 2/(N d) * r_{q+1}."""
+    def _backward(self, x, idx, cb, nq, g_out, g_commit, need_x, need_cb, som_t=None):
+        """rvq_backward: gx = g_out + g_commit * w * 2/(N d) * sum_q r_{q+1}; gcb[q, idx] -= g_commit * 2/(N d) * r_{q+1};
+        with ``use_som`` the codebook gradient is spread over each code's map neighbourhood (rvq_som_spread), so the
+        neighbours of a winner follow it - the SOM coupling for gradient-trained ("base") codebooks, ASSUMED."""
         lib = _lib.load()
         xf = x.detach()
         if xf.dtype != torch.float32:
@@ -373,6 +410,18 @@ class ResidualQuantizer(nn.Module):
             _lib.check(lib.rvq_backward(_ptr(x3), N, L, sb, sl, sd, self.dim, nq, self.K, _ptr(cb), _ptr(idx.reshape(-1, nq)),
                                         _ptr(go), _ptr(gc), self.commitment_weight, 1.0 if need_cb else 0.0,
                                         _ptr(gx), _ptr(gcb), _stream()), "rvq_backward")
+            if gcb is not None and self.use_som:
+                t = self._update_step_index() if som_t is None else som_t
+                radius, w = som_weights(self.som_kernel_type, t, self.som_shrink)
+                hw = []
+                for q in range(nq):
+                    hw += list(approximate_square_root(self.codebook_sizes[q]))
+                g2 = torch.zeros_like(gcb)
+                zc = torch.zeros(2, self.num_quantizers, self.K, dtype=torch.float32, device=dev)
+                _lib.check(lib.rvq_som_spread(_ptr(gcb), _ptr(zc[0]), _ptr(g2), _ptr(zc[1]), (C.c_int * len(hw))(*hw),
+                                              nq, self.K, self.dim, radius, (C.c_float * len(w))(*w), _stream()),
+                           "rvq_som_spread")
+                gcb = g2
         if gx is not None:
             if add_later is not None:
                 gx = gx + add_later
@@ -387,12 +436,12 @@ class ResidualQuantizer(nn.Module):
             raise ValueError(f"n must be in [1, {self.num_quantizers}], got {nq}")
         if x.shape[-1] != self.dim:
             raise ValueError(f"last dimension must be {self.dim}, got {tuple(x.shape)}")
-        update = bool(update_codebook) and self.training and self.quantizer_class == "ema"
+        update = bool(update_codebook) and self.training     # "base" keeps usage counts / re-seeds too (A13)
         if torch.is_grad_enabled() and (x.requires_grad or (self.quantizer_class == "base" and
                                                             self.codebooks.requires_grad)):
             out, idx, commit = _RVQFunction.apply(x, self.codebooks, self, nq, update)
             return out, idx, commit
-        xq, idx, commit_sq = self._encode(x, nq, update)
+        xq, idx, commit_sq, _ = self._encode(x, nq, update)
         N = idx.numel() // nq
         w = self.commitment_weight + (1.0 if self.quantizer_class == "base" else 0.0)
         commit = (commit_sq.sum() * (w / max(N * self.dim, 1))).to(torch.float32)
@@ -474,48 +523,64 @@ class ResidualQuantizer(nn.Module):
 class HostEncoder:
     """End-to-end encode of HOST-resident frames: pinned host -> device -> RVQ -> codes back to pinned host.
 
-    Frames are cut into chunks that ride two CUDA streams so that the host->device copy of chunk i+1 and the
-    device->host copy of chunk i-1 overlap the kernel of chunk i.  This is the call a serving user makes
-    when latents arrive from another process; ``bench.py`` times it as the ``e2e`` figure.
+    Frames are cut into chunks that ride ``n_buffers`` CUDA streams so that the host->device copy of chunk i+1 and
+    the device->host copy of chunk i-1 overlap the kernel of chunk i.  This is the call a serving user makes when
+    latents arrive from another process; ``bench.py`` times it as the ``e2e`` figure.
+
+    ``packed=True`` returns the codes in their wire format (``rvq_pack_indices``: ``ceil(n * code_bits / 8)`` bytes per
+    frame instead of ``8 n``), which is what crosses PCIe back to the host.
     """
 
-    def __init__(self, quantizer: ResidualQuantizer, chunk_frames: int = 1 << 17, n_buffers: int = 3):
+    def __init__(self, quantizer: ResidualQuantizer, chunk_frames: int = 1 << 17, n_buffers: int = 3,
+                 packed: bool = False):
         self.q = quantizer
         self.chunk = int(chunk_frames)
         self.nbuf = int(n_buffers)
+        self.packed = bool(packed)
         self._streams = None
         self._bufs = None
 
     def _setup(self, dev, nq):
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.nbuf)]
+            self._done = [torch.cuda.Event() for _ in range(self.nbuf)]
             d = self.q.dim
             self._bufs = [torch.empty(self.chunk, d, dtype=torch.float32, device=dev) for _ in range(self.nbuf)]
             self._wss = [torch.empty_like(self.q._workspace(dev)) for _ in range(self.nbuf)]
 
+    def bytes_per_frame(self, n: Optional[int] = None) -> int:
+        nq = self.q.num_quantizers if n is None else int(n)
+        return _lib.load().rvq_packed_bytes_per_frame(nq, self.q.code_bits) if self.packed else 8 * nq
+
     @torch.no_grad()
-    def encode(self, x_host: torch.Tensor, idx_host: Optional[torch.Tensor] = None, n: Optional[int] = None):
-        """x_host: pinned (N, d) fp32 on the CPU; returns pinned int64 (N, nq) codes (host)."""
+    def encode(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, n: Optional[int] = None):
+        """x_host: pinned (N, d) fp32 on the CPU; returns pinned codes on the host, complete when the call returns:
+        int64 (N, nq), or uint8 (N, bytes_per_frame) with ``packed=True``."""
         q = self.q
         nq = q.num_quantizers if n is None else int(n)
         dev = q.codebooks.device
         N = x_host.shape[0]
-        if idx_host is None:
-            idx_host = torch.empty((N, nq), dtype=torch.int64).pin_memory()
+        if out_host is None:
+            out_host = (torch.empty((N, self.bytes_per_frame(nq)), dtype=torch.uint8) if self.packed
+                        else torch.empty((N, nq), dtype=torch.int64)).pin_memory()
         self._setup(dev, nq)
         q._prepared()                      # operands built on the current stream before the side streams start
         cur = torch.cuda.current_stream(dev)
         ready = torch.cuda.Event()
         ready.record(cur)
+        used = set()
         for i, s0 in enumerate(range(0, N, self.chunk)):
-            st = self._streams[i % self.nbuf]
-            buf = self._bufs[i % self.nbuf]
+            b = i % self.nbuf
+            st, buf = self._streams[b], self._bufs[b]
             m = min(self.chunk, N - s0)
             st.wait_event(ready)
             with torch.cuda.stream(st):
                 buf[:m].copy_(x_host[s0:s0 + m], non_blocking=True)
-                _, idx, _ = q._encode(buf[:m], nq, False, ws=self._wss[i % self.nbuf])
-                idx_host[s0:s0 + m].copy_(idx, non_blocking=True)
-        for st in self._streams:
-            cur.wait_stream(st)
-        return idx_host
+                _, idx, _, _ = q._encode(buf[:m], nq, False, ws=self._wss[b])
+                out_host[s0:s0 + m].copy_(q.pack_indices(idx) if self.packed else idx, non_blocking=True)
+                self._done[b].record(st)
+            used.add(b)
+        for b in used:
+            cur.wait_event(self._done[b])     # stream order for device-side consumers ...
+            self._done[b].synchronize()       # ... and the HOST may read the codes as soon as encode() returns
+        return out_host

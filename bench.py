@@ -36,6 +36,10 @@ WORKLOADS = {
                desc="BASELINE configs[3] at full size: 32 x 4096 codes, d=512, 2M frames per GPU (16M frames on 8 GPUs)"),
     "c5q": dict(nq=8, K=1024, d=512, frames=1 << 18, update=False,
                 desc="reference model default quantizer (8 x 1024, d=512), 256K frames per GPU"),
+    "c5": dict(nq=8, K=1024, d=512, frames=8 * 500, update=False,
+               desc="BASELINE configs[4]: causal conv encoder -> RVQ -> decoder on 8 x 10 s of 24 kHz audio per GPU "
+                    "(64 x 10 s on 8 GPUs); conv stacks = scripts/c5_harness.py stand-in with the reference's channel / "
+                    "stride plan (out of scope as kernels: torch / cuDNN)"),
 }
 SPEC_BF16_TFLOPS = 2250.0
 
@@ -79,11 +83,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.proc = None
+
+    def window(self, t0, t1):
+        """Clock summary of the samples taken between wall-clock times t0 and t1 (the sampler keeps running)."""
         if self.proc is None:
             return None
         time.sleep(0.15)
-        self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
@@ -153,54 +162,48 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--algo", default="tensor")
-    args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
-    if args.frames:
-        wl["frames"] = args.frames
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        return run_reference(args, wl, rank, world)
+def bind_to_gpu_numa(local):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off, so that
+    concurrent host<->device copies of several ranks do not all cross one memory controller / PCIe root."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        devs = [d for d in os.listdir("/sys/bus/pci/devices") if d.lower().startswith("%04x:%02x:" % (dom, bus))]
+        node = int(open(f"/sys/bus/pci/devices/{devs[0]}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
+
+def build_quantizer(wl, dev, args):
     import torch
-    import torch.distributed as dist
     from audio_generation_b200 import ResidualQuantizer
-    from audio_generation_b200.quantizer import HostEncoder
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the RVQ path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
-    peaks = load_peaks()
-    nq, K, d, N = wl["nq"], wl["K"], wl["d"], wl["frames"]
-
+    nq, K, d = wl["nq"], wl["K"], wl["d"]
     # c2/c3 time the north-star path (encode [+ EMA count/sum, all-reduce, refresh]); the SOM neighbourhood and
     # stale-code re-seeding of SURVEY 8f are switched on by the c3m workload only
     quant = ResidualQuantizer(nq, d, "ema", K, algo=args.algo, use_som=bool(wl.get("som", False)),
-                              vq_cutoff_freq=float(wl.get("cutoff", 0.0)))
+                              vq_cutoff_freq=float(wl.get("cutoff", 0.0)), kernel=args.kernel)
     with torch.no_grad():
         quant.codebooks.copy_(synth_codebooks(nq, K, d))
         quant.ema_sum.copy_(quant.codebooks)
     quant = quant.to(dev)
     quant.train(wl["update"])
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.randn(N, d, device=dev, generator=g)
+    return quant
+
+
+def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, sampler=None):
+    """W (+ clock-settling) untimed steps, then exactly `steps` timed steps bracketed by barrier + synchronize;
+    device time = max over ranks.  Returns a dict of the raw numbers."""
+    import torch
+    import torch.distributed as dist
 
     def step():
         with torch.no_grad():
@@ -208,12 +211,7 @@ def main():
 
     # EMA workloads start from synthetic codebooks that the first updates pull towards the data (near-degenerate
     # codebooks, many exact re-ranks): time the steady state, not that transient
-    n_warm = max(args.warmup, 40 if wl["update"] else 3)
-    # the clock sampler (nvidia-smi -lms) starts BEFORE the warm-up: its start-up (NVML initialisation) was seen to
-    # stall kernel launches for tens of milliseconds when it fell into the timed region; rows are filtered by time
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    n_warm = max(warmup, 40 if wl["update"] else 3)
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0.record()
     out = None
@@ -236,22 +234,258 @@ def main():
         torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     quant.kernel_events = []          # (start, stop) CUDA events around every rvq_encode launch, on the launch stream
+    quant.comm_events = []            # ... and around every all-reduce of the statistics
     t_wall0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = step()
     ev1.record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
-    ms = ev0.elapsed_time(ev1)
+    del out
+    ms_local = ev0.elapsed_time(ev1)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.kernel_events)
-    quant.kernel_events = None
+    comm_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.comm_events) if quant.comm_events else 0.0
+    quant.kernel_events = quant.comm_events = None
+    ms = ms_local
+    per_rank = None
+    if world > 1:
+        t = torch.tensor([ms_local, kernel_ms, comm_ms], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        dist.barrier()
+        per_rank = [[float(v) for v in a.tolist()] for a in allt]
+        ms = max(p[0] for p in per_rank)
+    return dict(ms=ms, ms_local=ms_local, kernel_ms=kernel_ms, comm_ms=comm_ms, n_warm=n_warm, per_rank=per_rank,
+                wall=(t_wall0, t_wall1))
+
+
+def replicas_identical(quant, world, dev):
+    """True if every rank holds bit-identical codebooks and EMA state (what scripts/dist_check.py asserts)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return True
+    sig = torch.stack([quant.codebooks.detach().view(torch.int32).to(torch.int64).sum(),
+                       quant.ema_count.view(torch.int32).to(torch.int64).sum(),
+                       quant.ema_sum.view(torch.int32).to(torch.int64).sum()])
+    alls = [torch.zeros_like(sig) for _ in range(world)]
+    dist.all_gather(alls, sig)
+    return all(bool(torch.equal(a, alls[0])) for a in alls)
+
+
+def collective_leg(args, rank, world, local, dev, sampler):
+    """BASELINE configs[2] under the driver's own launch: c3 = encode + EMA statistics + all-reduce + refresh, the only
+    step of the path that crosses frame shards (training.py:305-308,325-328 -> vae.py:315-318)."""
+    import torch
+    import torch.distributed as dist
+    wl = dict(WORKLOADS["c3"])
+    if args.frames:
+        wl["frames"] = args.frames
+    nq, K, d, N = wl["nq"], wl["K"], wl["d"], wl["frames"]
+    quant = build_quantizer(wl, dev, args)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    x = torch.randn(N, d, device=dev, generator=g)
+    steps = max(5, min(args.steps, 20))
+    r = timed_steps(quant, x, wl, steps, args.warmup, rank, world, dev)
+    parity = replicas_identical(quant, world, dev)
+    clocks = sampler.window(*r["wall"]) if sampler is not None else None
+    # the same step with the all-reduce skipped (every rank updates from its own shard): what this GPU does on
+    # its own while its neighbours are just as busy - the denominator of the collective's efficiency
+    local_rate = None
+    if world > 1:
+        quant.sync_stats = False
+        r0 = timed_steps(quant, x, wl, steps, 3, rank, world, dev)
+        quant.sync_stats = True
+        local_rate = N * world * steps / (r0["ms"] * 1e-3)
+    all_clocks = None
+    if world > 1:
+        all_clocks = [None] * world
+        dist.all_gather_object(all_clocks, clocks)
+    else:
+        all_clocks = [clocks]
+    value = N * world * steps / (r["ms"] * 1e-3)
+    flops_per_frame = nq * 2 * K * d
+    peaks = load_peaks()
+    kms = [p[1] for p in r["per_rank"]] if r["per_rank"] else [r["kernel_ms"]]
+    cms = [p[2] for p in r["per_rank"]] if r["per_rank"] else [r["comm_ms"]]
+    ms_step = r["ms"] / steps
+    out = dict(workload="c3", desc=wl["desc"], value=value, unit="frames/s", per_gpu_value=value / world,
+               steps=steps, ms_per_step=ms_step, frames_per_gpu=N,
+               kernel_ms_min=min(kms), kernel_ms_max=max(kms), kernel_ms_per_rank=kms,
+               allreduce_ms=max(cms), allreduce_ms_per_rank=cms,
+               k0_k3_ms=max(0.0, ms_step - max(kms) - max(cms)),
+               k0_k3_note="step time minus the slowest rank's encode kernel and all-reduce: rvq_ema_finalize (K3), "
+                          "rvq_prepare_codebooks (K0), the statistics memset and launch gaps",
+               payload_bytes=nq * K * (d + 1) * 4,
+               value_without_allreduce=local_rate,
+               efficiency_vs_local_update=(value / local_rate) if local_rate else None,
+               roofline_frac=N * flops_per_frame / (max(kms) * 1e-3) / 1e12 / peaks["bf16"],
+               clocks_per_rank=all_clocks, parity="ok" if parity else "REPLICAS DIFFER")
+    del quant, x
+    torch.cuda.empty_cache()
+    return out
+
+
+def latency_leg(args, dev):
+    """Microseconds per `forward` through the module at the call shapes the reference really makes, the CPU oracle
+    beside each (same codebooks, same input)."""
+    import torch
+    from audio_generation_b200 import ResidualQuantizer
+    from oracle import rvq_oracle as O
+    shapes = [
+        dict(name="training call (training.py:296-328): B=4, L=150, d=512, nq=10, K=512, (B,d,L)-backed view, "
+                  "update_codebook=True", B=4, L=150, d=512, nq=10, K=512, update=True),
+        dict(name="C1 fixture shape (om.wav through config/training.yml): 1 x 136 x 512, nq=10, K=512, encode",
+             B=1, L=136, d=512, nq=10, K=512, update=False),
+        dict(name="C5 share of one GPU (8 x 10 s @ 24 kHz): 8 x 500 x 512, model default nq=8, K=1024, encode",
+             B=8, L=500, d=512, nq=8, K=1024, update=False),
+    ]
+    out = []
+    for sh in shapes:
+        torch.manual_seed(0)
+        q = ResidualQuantizer(sh["nq"], sh["d"], "ema", sh["K"], use_som=False, vq_cutoff_freq=0.0, kernel=args.kernel)
+        ref = O.ResidualQuantizerRef(sh["nq"], sh["d"], "ema", sh["K"], use_som=False, vq_cutoff_freq=0.0)
+        ref.load_state_dict({k: v for k, v in q.state_dict().items() if k in ref.state_dict()}, strict=False)
+        q = q.to(dev).train(sh["update"])
+        ref.train(sh["update"])
+        xc = torch.randn(sh["B"], sh["d"], sh["L"])
+        xv = xc.to(dev).permute(0, 2, 1)              # the reference's "b c l -> b l c" view (vae.py:313)
+        with torch.no_grad():
+            for _ in range(20):
+                q(xv, None, update_codebook=sh["update"])
+            torch.cuda.synchronize()
+            reps = 200
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(reps):
+                q(xv, None, update_codebook=sh["update"])
+            e1.record()
+            torch.cuda.synchronize()
+            wall_us = (time.perf_counter() - t0) / reps * 1e6
+            dev_us = e0.elapsed_time(e1) / reps * 1e3
+            xr = xc.permute(0, 2, 1)
+            ref(xr, None, update_codebook=sh["update"])
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ref(xr, None, update_codebook=sh["update"])
+            cpu_us = (time.perf_counter() - t0) / 3 * 1e6
+        out.append(dict(shape=sh["name"], frames=sh["B"] * sh["L"], us_per_call_device=dev_us,
+                        us_per_call_host_wall=wall_us, cpu_oracle_us_per_call=cpu_us, cpu_threads=torch.get_num_threads()))
+        del q
+    return out
+
+
+def run_c5(args, wl, rank, world, local, dev):
+    """BASELINE configs[4]: the whole model step around the drop-in (encoder -> "b c l -> b l c" view -> quantizer ->
+    decoder), 8 waveforms of 10 s per GPU, inference forward; reports how much of the step the RVQ path is."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from c5_harness import SyntheticCausalVQAE
+    torch.manual_seed(0)
+    model = SyntheticCausalVQAE(num_quantizers=wl["nq"], codebook_size=wl["K"]).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    B, T = 8, 240000
+    x = torch.randn(B, 1, T, device=dev, generator=g) * 0.1
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def step():
+        with torch.no_grad():
+            return model(x)
+
+    for _ in range(max(3, args.warmup)):
+        y, commit, index = step()
+    torch.cuda.synchronize()
+    frames = index.shape[0] * index.shape[1]
+    if world > 1:
+        dist.barrier()
+    model.quantizer.kernel_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    kms = statistics.mean(a.elapsed_time(b) for a, b in model.quantizer.kernel_events)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
         ms = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = sampler.window(t0, t1)
+    sampler.stop()
+    if rank == 0:
+        out = dict(metric="rvq_frames_per_sec", value=frames * world * args.steps / (ms * 1e-3), unit="frames/s",
+                   n_gpus=world, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms / args.steps,
+                   higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 convs (cuDNN) + f16-filter/f32-exact RVQ",
+                   data="synthetic", config=dict(workload="c5", desc=wl["desc"], nq=wl["nq"], K=wl["K"], d=wl["d"],
+                                                 waveforms_per_gpu=B, samples=T, frames_per_gpu=frames),
+                   rvq=dict(kernel_ms=kms, share_of_step=kms / (ms / args.steps), frames_per_call=frames,
+                            index_shape=list(index.shape)),
+                   gpu_launches=args.steps, clocks=clocks)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-collective", action="store_true", help="skip the c3 (encode + EMA + all-reduce) leg")
+    ap.add_argument("--no-latency", action="store_true", help="skip the small-call latency leg")
+    ap.add_argument("--algo", default="tensor")
+    ap.add_argument("--kernel", default="auto", help="auto | tmem | generic | frame (cross-check kernels)")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.frames:
+        wl["frames"] = args.frames
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, wl, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from audio_generation_b200.quantizer import HostEncoder
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the RVQ path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line only
+        dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "c5":
+        return run_c5(args, wl, rank, world, local, dev)
+    peaks = load_peaks()
+    nq, K, d, N = wl["nq"], wl["K"], wl["d"], wl["frames"]
+
+    quant = build_quantizer(wl, dev, args)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(N, d, device=dev, generator=g)
+    # the clock sampler (nvidia-smi -lms) starts BEFORE the warm-up: its start-up (NVML initialisation) was seen to
+    # stall kernel launches for tens of milliseconds when it fell into the timed region; rows are filtered by time.
+    # One sampler per rank, each on its own GPU.
+    sampler = ClockSampler(local)
+    sampler.start()
+    r = timed_steps(quant, x, wl, args.steps, args.warmup, rank, world, dev)
+    ms, kernel_ms, n_warm = r["ms"], r["kernel_ms"], r["n_warm"]
+    clocks = sampler.window(*r["wall"])
     frames_total = N * world * args.steps
     value = frames_total / (ms * 1e-3)
     ms_per_step = ms / args.steps
@@ -294,29 +528,51 @@ def main():
     if not args.no_e2e and not wl["update"]:
         n_e2e = min(N, 1 << 19)
         xh = torch.randn(n_e2e, d).pin_memory()
-        ih = torch.empty((n_e2e, nq), dtype=torch.int64).pin_memory()
-        he = HostEncoder(quant.eval())
+        he = HostEncoder(quant.eval(), packed=True)     # codes cross PCIe in their wire format (10 bits per code)
+        bpf = he.bytes_per_frame(nq)
+        ih = torch.empty((n_e2e, bpf), dtype=torch.uint8).pin_memory()
         for _ in range(3):
             he.encode(xh, ih)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = max(3, min(args.steps, 10))
+        # HostEncoder.encode returns when the codes are on the host: host wall clock around the calls IS the end-to-end
+        # time; the device events bracket the same region
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(reps):
             he.encode(xh, ih)
         e1.record()
         torch.cuda.synchronize()
-        ems = e0.elapsed_time(e1)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ems = max(e0.elapsed_time(e1), wall_ms)
+        h2d_gbs = n_e2e * d * 4 * reps / (ems * 1e-3) / 1e9
         if world > 1:
             t = torch.tensor([ems], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank_gbs = [n_e2e * d * 4 * reps / (float(a.item()) * 1e-3) / 1e9 for a in allt]
+            ems = max(float(a.item()) for a in allt)
+        else:
+            per_rank_gbs = [h2d_gbs]
         e2e = dict(value=n_e2e * world * reps / (ems * 1e-3), unit="frames/s",
-                   h2d_bytes_per_step=n_e2e * d * 4, d2h_bytes_per_step=n_e2e * nq * 8,
-                   frames_per_step=n_e2e, api="audio_generation_b200.quantizer.HostEncoder.encode")
+                   h2d_bytes_per_step=n_e2e * d * 4, d2h_bytes_per_step=n_e2e * bpf,
+                   frames_per_step=n_e2e, h2d_gbs_per_rank=per_rank_gbs, numa_node=numa,
+                   api="audio_generation_b200.quantizer.HostEncoder(packed=True).encode: pinned host frames in, packed "
+                       "codes on the host when the call returns")
         quant.train(wl["update"])
+
+    del x
+    torch.cuda.empty_cache()
+    collective = None
+    if not args.no_collective and args.workload == "c2":
+        collective = collective_leg(args, rank, world, local, dev, sampler)
+    sampler.stop()
+    latency = None
+    if rank == 0 and world == 1 and not args.no_latency and args.workload == "c2":
+        latency = latency_leg(args, dev)
 
     if rank != 0:
         if world > 1:
@@ -326,17 +582,24 @@ def main():
     flops_per_frame = nq * 2 * K * d
     per_gpu_rate = value / world
     achieved = N * flops_per_frame / (kernel_ms * 1e-3) / 1e12      # the fused encode kernel alone (rank 0)
-    traffic = None
+    traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            tj = json.load(open(tp))
+            traffic = tj.get(args.workload)
+            traffic_src = tj.get("_source")
         except Exception:
             traffic = None
+    kname = {"tmem": "rvq_encode_tr_kernel", "frame": "rvq_encode_fr_kernel", "generic": "rvq_encode_tc_kernel"}.get(
+        args.kernel, "rvq_encode_tr_kernel" if d <= 128 else "rvq_encode_tc_kernel")
     roofline = dict(bound="tensor", achieved=achieved, peak=peaks["bf16"], unit="TFLOP/s", frac=achieved / peaks["bf16"],
-                    traffic=traffic, peak_source=peaks["source"] + " (burst bf16 cuBLAS 8192^3)",
+                    traffic=traffic,
+                    traffic_source=(traffic_src or "profiles/traffic.json") + " (dram__bytes_read+write of one earlier "
+                                   "`ncu --set full` capture of this kernel at this size; NOT measured by this run)",
+                    peak_source=peaks["source"] + " (burst bf16 cuBLAS 8192^3)",
                     frac_of_sustained=achieved / peaks["bf16_sustained"], frac_of_spec=achieved / SPEC_BF16_TFLOPS,
-                    kernel="rvq_encode_tr_kernel" if d <= 128 else "rvq_encode_tc_kernel", flops_per_frame=flops_per_frame,
+                    kernel=kname, flops_per_frame=flops_per_frame,
                     kernel_ms=kernel_ms, step_frac_of_peak=per_gpu_rate * flops_per_frame / 1e12 / peaks["bf16"],
                     note="algorithmic flops = nq*2*K*d per frame (distance GEMM only); achieved = frames per launch x "
                          "flops per frame / mean launch duration of the fused encode kernel (CUDA events on the launch "
@@ -354,13 +617,17 @@ def main():
     # and k0_stage_max + k0_convert (operands of the refreshed codebooks); c3m adds som_spread, reseed_gather/apply
     launches_per_step = 1 + (4 if wl["update"] else 0) + (1 if wl.get("som") else 0) + (2 if wl.get("cutoff") else 0)
     out = dict(metric="rvq_frames_per_sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps,
-               warmup=n_warm, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+               warmup=args.warmup, warmup_extra=n_warm - args.warmup,
+               warmup_note="the W requested warm-up steps plus `warmup_extra` untimed clock-settling steps (~0.4 s of "
+                           "this kernel); the timed region is exactly `steps` steps",
+               ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
                vs_baseline=None, dtype="f16-filter/f32-exact", data="synthetic",
                config=dict(workload=args.workload, desc=wl["desc"], nq=nq, K=K, d=d, frames_per_gpu=N,
                            update_codebook=wl["update"], parallelism=f"frames sharded x{world}, codebooks replicated",
-                           l2="inputs (%.0f MB) larger than L2; no explicit flush" % (N * d * 4 / 1e6), algo=args.algo),
+                           l2="inputs (%.0f MB) larger than L2; no explicit flush" % (N * d * 4 / 1e6), algo=args.algo,
+                           kernel=args.kernel),
                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=args.steps * launches_per_step,
-               clocks=clocks)
+               clocks=clocks, collective=collective, latency=latency)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -269,6 +269,25 @@ def reseed_apply_ref(cb, ema_count, ema_sum, rep, cutoff: float, reset_count: fl
     return cb, ema_count, ema_sum, int(stale.sum())
 
 
+class _SomGradSpread(torch.autograd.Function):
+    """Identity on a stage's codebook whose BACKWARD spreads the gradient over each code's map neighbourhood
+    (``som_spread_ref``): the SOM coupling for gradient-trained (``quantizer_class="base"``) codebooks - the
+    neighbours of a winning code are pulled along with it.  ASSUMED (the reference's config/training.yml:15-21 asks
+    for ``vq_type: "base"`` with ``use_som: True``; the package that defines it is absent)."""
+
+    @staticmethod
+    def forward(ctx, cb, height, width, radius, weights):
+        ctx.geom = (height, width, radius, weights)
+        return cb.view_as(cb)
+
+    @staticmethod
+    def backward(ctx, g):
+        import numpy as np
+        h, w, radius, weights = ctx.geom
+        gs, _ = som_spread_ref(g.detach().cpu().numpy(), np.zeros(g.shape[0], dtype=np.float32), h, w, radius, weights)
+        return torch.from_numpy(gs).to(g.device), None, None, None, None
+
+
 # --------------------------------------------------------------------------
 # nn.Module with the reference's call-site contract (SURVEY Appendix A)
 # --------------------------------------------------------------------------
@@ -337,6 +356,9 @@ class ResidualQuantizerRef(nn.Module):
         for q in range(nq):
             K = self.codebook_sizes[q]
             cb = self.codebooks[q, :K]
+            if self.quantizer_class == "base" and self.use_som and cb.requires_grad:
+                radius, w = som_weights(self.som_kernel_type, int(self.update_steps), self.som_shrink)
+                cb = _SomGradSpread.apply(cb, *approximate_square_root(K), radius, w)
             with torch.no_grad():
                 i = stage_scores(r.detach(), cb.detach()).argmin(dim=1)
             z = cb[i]
@@ -365,6 +387,30 @@ class ResidualQuantizerRef(nn.Module):
                         sm, cnt = torch.from_numpy(sm_), torch.from_numpy(cnt_)
                     ncb, nc, ns = ema_finalize_ref(cb, self.ema_count[q, :K], self.ema_sum[q, :K], cnt, sm,
                                                    self.decay, self.eps)
+                    if rep is not None:
+                        ncb, nc, ns, nrep = reseed_apply_ref(ncb, nc, ns, rep, self.vq_cutoff_freq,
+                                                             self.vq_cutoff_freq)
+                        self.n_replaced[q] = nrep
+                    self._pending = getattr(self, "_pending", [])
+                    self._pending.append((q, K, ncb, nc, ns))
+            if update_codebook and self.training and self.quantizer_class == "base":
+                # gradient-trained codebooks (training.py:305-308 passes update_codebook=True for them too): only the
+                # usage counts are averaged and stale codes re-seeded; ASSUMED
+                with torch.no_grad():
+                    cnt, _ = ema_stats_ref(r.detach(), i, K)
+                    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+                    rank = torch.distributed.get_rank() if dist_on else 0
+                    world = torch.distributed.get_world_size() if dist_on else 1
+                    rep = None
+                    if self.vq_cutoff_freq > 0:
+                        rep = reseed_vectors_ref(r.detach(), q, max(self.codebook_sizes), self.step_seed(),
+                                                 rank * N, N * world)[:K]
+                    if dist_on:
+                        torch.distributed.all_reduce(cnt)
+                        if rep is not None:
+                            torch.distributed.all_reduce(rep)
+                    nc = self.decay * self.ema_count[q, :K] + (1.0 - self.decay) * cnt
+                    ncb, ns = self.codebooks.detach()[q, :K].clone(), self.ema_sum[q, :K].clone()
                     if rep is not None:
                         ncb, nc, ns, nrep = reseed_apply_ref(ncb, nc, ns, rep, self.vq_cutoff_freq,
                                                              self.vq_cutoff_freq)

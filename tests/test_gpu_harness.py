@@ -49,8 +49,7 @@ def test_model_trains_through_the_drop_in(vq_type):
         assert model.enc[0].weight.grad is not None and torch.isfinite(model.enc[0].weight.grad).all()
         if vq_type == "base":
             assert model.quantizer.codebooks.grad is not None
-        opt.step()
-        model.quantizer.invalidate()          # "base": the optimiser wrote the codebooks in place
+        opt.step()          # "base": the optimiser writes the codebooks in place; the module notices by itself
         losses.append(float(loss))
     assert index.dtype == torch.int64 and index.shape[:2] == (4, 256)
     assert losses[-1] < losses[0]
@@ -65,3 +64,33 @@ def test_model_trains_through_the_drop_in(vq_type):
     for i in range(model.quantizer.num_quantizers):
         z = z + model.quantizer.quantizers[i].dequantize(idx[:1, :, i])
     assert z.shape == (1, 256, 128)
+
+
+def test_c5_shape_plan_model_with_the_references_training_config():
+    """BASELINE configs[4] / config/training.yml:13-21: the conv stand-in with the reference's channel and stride plan
+    (scripts/c5_harness.py), quantizer built from the yml's vae_args (10 x 512 codes, vq_type "base", use_som, cutoff
+    0.1), one training step the way training.py:325-346 does it and the eval path, on the real latent layout."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from c5_harness import SyntheticCausalVQAE
+    torch.manual_seed(0)
+    model = SyntheticCausalVQAE(num_quantizers=10, codebook_size=512, vq_type="base", vq_cutoff_freq=0.1, use_som=True,
+                                som_kernel_type="hard", width=0.25).cuda().train()
+    x = torch.randn(4, 1, 72000, device="cuda") * 0.1                 # training.py:310-311: (B=4, 1, 72000) -> L = 150
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    for codebook_n in (10, 3):                                        # training.py:283-294: stage count varies per call
+        opt.zero_grad()
+        y, commit, index = model(x, update_codebook=True, codebook_n=codebook_n)
+        assert y.shape == x.shape and index.shape == (4, 150, codebook_n) and index.dtype == torch.int64
+        loss = torch.nn.functional.mse_loss(y, x) + commit
+        loss.backward()
+        assert torch.isfinite(loss) and model.quantizer.codebooks.grad is not None
+        assert torch.isfinite(model.stem.conv.weight.grad).all()
+        opt.step()
+    assert len(model.quantizer.get_stale_clusters()) == 10            # training.py:435,461
+    model.quantizer.update_cutoff(ratio=0.95)                         # training.py:454
+    model.eval()
+    with torch.no_grad():
+        y, commit, index = model(x[:1])
+    assert index.shape == (1, 150, 10)

@@ -249,3 +249,38 @@ def test_codebook_maintenance_properties():
     assert len(set(fr)) > 0.7 * N                      # 1024 draws over 600 frames hit most of them
     assert fr != [O.reseed_frame_ref(100, 3, K, k, N) for k in range(K)]
     assert fr != [O.reseed_frame_ref(99, 4, K, k, N) for k in range(K)]
+
+
+def test_base_class_keeps_usage_counts_reseeds_and_spreads_gradient():
+    """quantizer_class="base" with update_codebook=True (what config/training.yml + training.py:305-308 ask for):
+    usage counts are averaged, stale codes re-seeded, the codebooks otherwise only move by gradient, and with use_som
+    the gradient of a winning code reaches its four map neighbours with weight sigma_t."""
+    torch.manual_seed(0)
+    nq, K, d = 2, 16, 8
+    m = O.ResidualQuantizerRef(nq, d, "base", K, vq_cutoff_freq=0.0, use_som=True, som_kernel_type="hard")
+    m.train()
+    cb0 = m.codebooks.detach().clone()
+    x = torch.randn(1, 40, d)
+    _, idx, commit = m(x, None, update_codebook=True)
+    commit.backward()
+    assert torch.equal(m.codebooks.detach(), cb0)                        # no EMA refresh for "base"
+    cnt = torch.bincount(idx[0, :, 0], minlength=K).float()
+    assert torch.allclose(m.ema_count[0], 0.99 * torch.ones(K) + 0.01 * cnt)
+    assert int(m.update_steps) == 1
+    # gradient spreading: a code nobody selected still receives gradient if a grid neighbour was selected
+    h, w = O.approximate_square_root(K)
+    g = m.codebooks.grad[0]
+    hit = cnt > 0
+    for k in range(K):
+        y, xg = divmod(k, w)
+        nb = [(y + dy) * w + (xg + dx) for dy, dx in ((-1, 0), (1, 0), (0, -1), (0, 1))
+              if 0 <= y + dy < h and 0 <= xg + dx < w]
+        reached = bool(hit[k]) or any(bool(hit[n]) for n in nb)
+        assert (g[k].abs().sum() > 0) == reached
+    # re-seeding: with a cutoff above every count all codes are replaced by residual rows
+    m2 = O.ResidualQuantizerRef(nq, d, "base", K, vq_cutoff_freq=5.0, use_som=False)
+    m2.train()
+    m2(x, None, update_codebook=True)
+    assert m2.n_replaced == [K, K] and m2.get_stale_clusters() == [0, 0]
+    rows = x.reshape(-1, d)
+    assert all(any(torch.equal(m2.codebooks[0, k].detach(), r) for r in rows) for k in range(K))
