@@ -199,18 +199,20 @@ class ResidualQuantizer(nn.Module):
         self.register_load_state_dict_post_hook(_forget_step_mirror)
         self.quantizers = [_Stage(self, q) for q in range(self.num_quantizers)]
         self._derived = None       # (key, cb_op, cb_norm, cb_meta)
+        self._derived_bufs = None  # the three buffers, reused across rebuilds (stream-ordered: one stream per module)
         self._ws = None
         self._stats = None
         self._spread = None
         self.last_stats = None     # flat [sum | cnt | replacement vectors] of the most recent update (for inspection)
         self.kernel_events = None  # a list collects (start, stop) CUDA events around every rvq_encode launch (bench.py)
-        self.comm_events = None    # ... and around every all-reduce of the statistics
+        self.comm_events = None    # ... around every all-reduce of the statistics
+        self.update_events = None  # ... and around the whole codebook maintenance that follows the kernel
         self.sync_stats = True     # False: every rank updates from its own shard only (replicas DIVERGE; measurements)
 
     # ------------------------------------------------------------------ derived operands / scratch
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._derived = self._ws = self._stats = self._spread = self._steps_host = None
+        self._derived = self._derived_bufs = self._ws = self._stats = self._spread = self._steps_host = None
         return out
 
     def _check_device(self, t: torch.Tensor):
@@ -220,20 +222,38 @@ class ResidualQuantizer(nn.Module):
             raise RVQError(f"input on {t.device} but codebooks on {self.codebooks.device}")
 
     def invalidate(self):
-        """Call after writing ``codebooks`` in place outside this class."""
+        """Call after writing ``codebooks`` in place outside this class by means that do not bump the tensor's version
+        counter while the module is in eval mode (nothing in the reference does)."""
         self._derived = None
 
+    def train(self, mode: bool = True):
+        # whatever a fused optimizer wrote while training is picked up by the first eval-mode call (training.py:494-499)
+        if mode != self.training:
+            self._derived = None
+        return super().train(mode)
+
     def _prepared(self):
+        """fp16 operands / norms / metadata of the current codebooks (K0), rebuilt when the codebooks changed.
+
+        Buffers ("ema") only change through this class.  Parameters ("base") are rewritten in place by the optimizer:
+        foreach / for-loop optimizers bump the tensor's version counter, but FUSED ones (torch._fused_adam_) do not
+        (measured: tests/test_gpu_hardening.py), so in training mode gradient-trained codebooks are re-prepared on every
+        call (two small HBM-bound kernels over nq K d floats); in eval mode the (pointer, version) key is used."""
         cb = self.codebooks.detach()
         key = (cb.data_ptr(), cb._version, str(cb.device))
-        if self._derived is None or self._derived[0] != key:
+        always = self.quantizer_class == "base" and self.training
+        if self._derived is None or self._derived[0] != key or always:
             lib = _lib.load()
             nq, K, d = self.num_quantizers, self.K, self.dim
-            ob, nb, mb = C.c_size_t(), C.c_size_t(), C.c_size_t()
-            _lib.check(lib.rvq_prepared_bytes(nq, K, d, C.byref(ob), C.byref(nb), C.byref(mb)), "rvq_prepared_bytes")
-            op = torch.empty(ob.value // 2, dtype=torch.float16, device=cb.device)
-            nrm = torch.empty(nb.value // 4, dtype=torch.float32, device=cb.device)
-            meta = torch.empty(mb.value // 4, dtype=torch.float32, device=cb.device)
+            bufs = self._derived_bufs
+            if bufs is None or bufs[0].device != cb.device:
+                ob, nb, mb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+                _lib.check(lib.rvq_prepared_bytes(nq, K, d, C.byref(ob), C.byref(nb), C.byref(mb)), "rvq_prepared_bytes")
+                bufs = (torch.empty(ob.value // 2, dtype=torch.float16, device=cb.device),
+                        torch.empty(nb.value // 4, dtype=torch.float32, device=cb.device),
+                        torch.empty(mb.value // 4, dtype=torch.float32, device=cb.device))
+                self._derived_bufs = bufs
+            op, nrm, meta = bufs
             with torch.cuda.device(cb.device):
                 _lib.check(lib.rvq_prepare_codebooks(_ptr(cb), _ptr(self.k_valid), nq, K, d, _ptr(op), _ptr(nrm),
                                                      _ptr(meta), _stream()), "rvq_prepare_codebooks")
@@ -374,6 +394,10 @@ class ResidualQuantizer(nn.Module):
                     cb_used = cb.clone()
                 self._update_step_index()
                 self._update_codebooks(x3, N, L, sb, sl, sd, nq, idx, flat, ssum, scnt, rep)
+                if self.update_events is not None and self.kernel_events is not None:
+                    k2 = torch.cuda.Event(enable_timing=True)
+                    k2.record()
+                    self.update_events.append((k1, k2))
         xq = xq.reshape(x.shape) if xq.shape != x.shape else xq
         return xq, idx.reshape(*x.shape[:-1], nq), commit_sq, cb_used
 

@@ -234,7 +234,8 @@ def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, sampler=None):
         torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     quant.kernel_events = []          # (start, stop) CUDA events around every rvq_encode launch, on the launch stream
-    quant.comm_events = []            # ... and around every all-reduce of the statistics
+    quant.comm_events = []            # ... around every all-reduce of the statistics
+    quant.update_events = []          # ... and around the codebook maintenance behind the kernel (all-reduce included)
     t_wall0 = time.time()
     ev0.record()
     for _ in range(steps):
@@ -246,18 +247,19 @@ def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, sampler=None):
     ms_local = ev0.elapsed_time(ev1)
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.kernel_events)
     comm_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.comm_events) if quant.comm_events else 0.0
-    quant.kernel_events = quant.comm_events = None
+    upd_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.update_events) if quant.update_events else 0.0
+    quant.kernel_events = quant.comm_events = quant.update_events = None
     ms = ms_local
     per_rank = None
     if world > 1:
-        t = torch.tensor([ms_local, kernel_ms, comm_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_local, kernel_ms, comm_ms, upd_ms], device=dev, dtype=torch.float64)
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         dist.barrier()
         per_rank = [[float(v) for v in a.tolist()] for a in allt]
         ms = max(p[0] for p in per_rank)
-    return dict(ms=ms, ms_local=ms_local, kernel_ms=kernel_ms, comm_ms=comm_ms, n_warm=n_warm, per_rank=per_rank,
-                wall=(t_wall0, t_wall1))
+    return dict(ms=ms, ms_local=ms_local, kernel_ms=kernel_ms, comm_ms=comm_ms, upd_ms=upd_ms, n_warm=n_warm,
+                per_rank=per_rank, wall=(t_wall0, t_wall1))
 
 
 def replicas_identical(quant, world, dev):
@@ -292,12 +294,13 @@ def collective_leg(args, rank, world, local, dev, sampler):
     clocks = sampler.window(*r["wall"]) if sampler is not None else None
     # the same step with the all-reduce skipped (every rank updates from its own shard): what this GPU does on
     # its own while its neighbours are just as busy - the denominator of the collective's efficiency
-    local_rate = None
+    local_rate = local_kms = None
     if world > 1:
         quant.sync_stats = False
         r0 = timed_steps(quant, x, wl, steps, 3, rank, world, dev)
         quant.sync_stats = True
         local_rate = N * world * steps / (r0["ms"] * 1e-3)
+        local_kms = [p[1] for p in r0["per_rank"]]
     all_clocks = None
     if world > 1:
         all_clocks = [None] * world
@@ -309,14 +312,17 @@ def collective_leg(args, rank, world, local, dev, sampler):
     peaks = load_peaks()
     kms = [p[1] for p in r["per_rank"]] if r["per_rank"] else [r["kernel_ms"]]
     cms = [p[2] for p in r["per_rank"]] if r["per_rank"] else [r["comm_ms"]]
+    ums = [p[3] for p in r["per_rank"]] if r["per_rank"] else [r["upd_ms"]]
     ms_step = r["ms"] / steps
     out = dict(workload="c3", desc=wl["desc"], value=value, unit="frames/s", per_gpu_value=value / world,
                steps=steps, ms_per_step=ms_step, frames_per_gpu=N,
                kernel_ms_min=min(kms), kernel_ms_max=max(kms), kernel_ms_per_rank=kms,
                allreduce_ms=max(cms), allreduce_ms_per_rank=cms,
-               k0_k3_ms=max(0.0, ms_step - max(kms) - max(cms)),
-               k0_k3_note="step time minus the slowest rank's encode kernel and all-reduce: rvq_ema_finalize (K3), "
-                          "rvq_prepare_codebooks (K0), the statistics memset and launch gaps",
+               update_ms_per_rank=ums, k0_k3_ms=max(u - c for u, c in zip(ums, cms)),
+               k0_k3_note="CUDA events from the end of the encode kernel to the end of the codebook maintenance "
+                          "(update_ms: all-reduce + rvq_ema_finalize K3 [+ SOM / re-seeding]); k0_k3_ms = that minus the "
+                          "all-reduce; rvq_prepare_codebooks (K0) runs at the start of the next call, inside ms_per_step",
+               kernel_ms_per_rank_without_allreduce=local_kms,
                payload_bytes=nq * K * (d + 1) * 4,
                value_without_allreduce=local_rate,
                efficiency_vs_local_update=(value / local_rate) if local_rate else None,
@@ -467,9 +473,20 @@ def main():
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"         # keep NCCL's version banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created (at NCCL_DEBUG=VERSION and WARN
+        # alike): stdout is pointed at stderr while that happens, so that rank 0 prints ONE JSON line and nothing else
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            t0 = torch.zeros(1, device=dev)
+            dist.all_reduce(t0)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     if args.workload == "c5":
         return run_c5(args, wl, rank, world, local, dev)
     peaks = load_peaks()

@@ -20,12 +20,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, cls="ema"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(7)
     nq, K, d, N = 3, 32, 16, 400
-    m = O.ResidualQuantizerRef(nq, d, "ema", K).train()
+    m = O.ResidualQuantizerRef(nq, d, cls, K).train()
     x = torch.randn(N, d)
     shard = x[rank * N // world:(rank + 1) * N // world]
     with torch.no_grad():
@@ -34,16 +34,22 @@ def _worker(rank, world, port, q):
     flat = torch.zeros(nq * K * d + nq * K)
     flat[rank::world] = 1.0
     dist.all_reduce(flat)
-    q.put((rank, m.codebooks.clone(), m.ema_count.clone(), idx.clone(), float(flat.sum())))
+    q.put((rank, m.codebooks.detach().clone(), m.ema_count.clone(), idx.clone(), float(flat.sum())))
     dist.destroy_process_group()
 
 
-def test_sharded_update_equals_single_process():
+import pytest
+
+
+@pytest.mark.parametrize("cls", ["ema", "base"])
+def test_sharded_update_equals_single_process(cls):
+    """"base" (gradient-trained codebooks): only the usage counts and the replacement vectors of stale codes cross the
+    shards, in the same single all-reduce."""
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, cls)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
@@ -51,12 +57,12 @@ def test_sharded_update_equals_single_process():
         p.join(60)
     torch.manual_seed(7)
     nq, K, d, N = 3, 32, 16, 400
-    ref = O.ResidualQuantizerRef(nq, d, "ema", K).train()
+    ref = O.ResidualQuantizerRef(nq, d, cls, K).train()
     x = torch.randn(N, d)
     with torch.no_grad():
         _, ridx, _ = ref(x, None, update_codebook=True)
     assert torch.equal(res[0][1], res[1][1])                           # replicas stay bit-identical
-    assert torch.allclose(res[0][1], ref.codebooks, rtol=1e-5, atol=1e-6)   # and equal the unsharded update
+    assert torch.allclose(res[0][1], ref.codebooks.detach(), rtol=1e-5, atol=1e-6)   # and equal the unsharded update
     assert torch.allclose(res[0][2], ref.ema_count, rtol=1e-6)
     assert torch.equal(torch.cat([res[0][3], res[1][3]]), ridx)        # encode needs no communication
     assert res[0][4] == nq * K * d + nq * K

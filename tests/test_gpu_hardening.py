@@ -48,7 +48,8 @@ def test_golden_c1_reference_latents_through_cuda():
     m = load_codebooks(quantizer(nq, K, d, "base", vq_cutoff_freq=0.1, use_som=True), cbs).cuda().eval()
     x = torch.from_numpy(z["x_fp16"]).float()                               # (1, 136, 512)
     xs = x.permute(0, 2, 1).contiguous().cuda().permute(0, 2, 1)            # channel-major storage, frame view
-    assert tuple(xs.shape) == tuple(z["x_shape"]) and tuple(xs.stride()) == tuple(z["x_stride"])
+    assert tuple(xs.shape) == tuple(z["x_shape"]) and not xs.is_contiguous()
+    assert tuple(xs.stride()[1:]) == tuple(int(v) for v in z["x_stride"][1:])   # (.., 1, 136); dim 0 has size 1
     with torch.no_grad():
         xq, idx, commit = m(xs, None)
     assert idx.shape == tuple(z["ref_index_shape"]) and idx.dtype == torch.int64
@@ -61,7 +62,7 @@ def test_golden_c1_reference_latents_through_cuda():
         # "base": commit = commitment + codebook loss = 2 x the per-stage means the fixture holds
         assert abs(float(commit) - 2.0 * float(z["commit"].sum())) <= 1e-5 * 2.0 * float(z["commit"].sum())
         assert abs(float(xq.double().sum()) - float(z["xq_checksum"])) < 1e-3 * max(1.0, abs(float(z["xq_checksum"])))
-    assert xq.stride() == xs.stride()                                       # decoder-side rearrange stays a view
+    assert xq.stride()[1:] == xs.stride()[1:]                               # decoder-side rearrange stays a view
 
 
 def test_golden_small_problem_through_cuda():
