@@ -207,6 +207,8 @@ class ResidualQuantizer(nn.Module):
         self.kernel_events = None  # a list collects (start, stop) CUDA events around every rvq_encode launch (bench.py)
         self.comm_events = None    # ... around every all-reduce of the statistics
         self.update_events = None  # ... and around the whole codebook maintenance that follows the kernel
+        self.comm_copy = False     # True: all-reduce a copy of the statistics instead of the kernel's own buffer
+        self._comm = None
         self.sync_stats = True     # False: every rank updates from its own shard only (replicas DIVERGE; measurements)
 
     # ------------------------------------------------------------------ derived operands / scratch
@@ -319,7 +321,17 @@ class ResidualQuantizer(nn.Module):
             if self.comm_events is not None:
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM)
+            if self.comm_copy:
+                # all-reduce a COPY: the buffer the encode kernel reduces into never becomes NCCL's send/receive buffer
+                if self._comm is None or self._comm.numel() != flat.numel() or self._comm.device != flat.device:
+                    self._comm = torch.empty_like(flat)
+                self._comm[lo:hi].copy_(flat[lo:hi])
+                dist.all_reduce(self._comm[lo:hi], op=dist.ReduceOp.SUM)
+                flat = self._comm
+                nsd = self.num_quantizers * K * d
+                ssum, scnt, rep = flat[:nsd], flat[nsd: nsd + self.num_quantizers * K], flat[nsd + self.num_quantizers * K:]
+            else:
+                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM)
             if self.comm_events is not None:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record()

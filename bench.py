@@ -209,9 +209,11 @@ def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, sampler=None):
         with torch.no_grad():
             return quant(x, None, update_codebook=wl["update"])
 
-    # EMA workloads start from synthetic codebooks that the first updates pull towards the data (near-degenerate
-    # codebooks, many exact re-ranks): time the steady state, not that transient
-    n_warm = max(warmup, 40 if wl["update"] else 3)
+    # EMA workloads start from synthetic codebooks that the updates pull towards the data with a time constant of
+    # 1 / (1 - decay) = 100 steps, and the kernel's time depends on the codebooks (how many frames need the exact
+    # re-rank): time the steady state, not that transient (profiles/r2b_c3_comm_probe_2gpu.log: the first 30 steps after
+    # the statistics change scale run 5 % slower than the steady state)
+    n_warm = max(warmup, 150 if wl["update"] else 3)
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0.record()
     out = None
@@ -297,7 +299,7 @@ def collective_leg(args, rank, world, local, dev, sampler):
     local_rate = local_kms = None
     if world > 1:
         quant.sync_stats = False
-        r0 = timed_steps(quant, x, wl, steps, 3, rank, world, dev)
+        r0 = timed_steps(quant, x, wl, steps, args.warmup, rank, world, dev)
         quant.sync_stats = True
         local_rate = N * world * steps / (r0["ms"] * 1e-3)
         local_kms = [p[1] for p in r0["per_rank"]]
@@ -371,6 +373,21 @@ def latency_leg(args, dev):
             torch.cuda.synchronize()
             wall_us = (time.perf_counter() - t0) / reps * 1e6
             dev_us = e0.elapsed_time(e1) / reps * 1e3
+            graph_us = None
+            if not sh["update"]:
+                # the same call captured once in a CUDA graph and replayed (launch + Python overhead removed)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    q(xv, None)
+                for _ in range(5):
+                    gr.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    gr.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                graph_us = e0.elapsed_time(e1) / reps * 1e3
             xr = xc.permute(0, 2, 1)
             ref(xr, None, update_codebook=sh["update"])
             t0 = time.perf_counter()
@@ -378,7 +395,8 @@ def latency_leg(args, dev):
                 ref(xr, None, update_codebook=sh["update"])
             cpu_us = (time.perf_counter() - t0) / 3 * 1e6
         out.append(dict(shape=sh["name"], frames=sh["B"] * sh["L"], us_per_call_device=dev_us,
-                        us_per_call_host_wall=wall_us, cpu_oracle_us_per_call=cpu_us, cpu_threads=torch.get_num_threads()))
+                        us_per_call_host_wall=wall_us, us_per_call_cuda_graph_replay=graph_us,
+                        cpu_oracle_us_per_call=cpu_us, cpu_threads=torch.get_num_threads()))
         del q
     return out
 

@@ -363,3 +363,27 @@ def test_sharded_update_two_ranks_torchrun():
                        env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "replicas_bit_identical=True" in r.stdout
+
+
+@pytest.mark.parametrize("d,L", [(512, 150), (128, 500)])
+def test_encode_call_is_cuda_graph_capturable(d, L):
+    """The eval-mode call (encode only) on the reference's strided latent view, captured once in a CUDA graph and
+    replayed on new inputs: same codes as the eager call (nothing on the path synchronises or allocates outside the
+    stream-ordered allocator)."""
+    m = quantizer(6, 512, d).cuda().eval()
+    static_x = torch.randn(4, d, L, device="cuda")
+    xv = static_x.permute(0, 2, 1)
+    with torch.no_grad():
+        m(xv)                                             # builds the operands and the workspace outside the capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            xq_g, idx_g, commit_g = m(xv)
+        for seed in (1, 2):
+            torch.manual_seed(seed)
+            static_x.copy_(torch.randn(4, d, L, device="cuda"))
+            g.replay()
+            torch.cuda.synchronize()
+            xq_e, idx_e, commit_e = m(xv)
+            assert torch.equal(idx_g, idx_e) and torch.equal(xq_g, xq_e)
+            assert abs(float(commit_g) - float(commit_e)) <= 1e-6 * abs(float(commit_e))
