@@ -62,16 +62,18 @@ def synth_codebooks(nq, K, d, seed=4321):
 
 
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """ONE `nvidia-smi -lms` process (started by rank 0) that samples EVERY GPU of the box: per-rank clocks without
+    one NVML client per rank (eight pollers were seen to perturb an 8-GPU step)."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self):
+        self.rows, self.proc = [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -88,27 +90,33 @@ class ClockSampler:
             self.proc.terminate()
             self.proc = None
 
-    def window(self, t0, t1):
-        """Clock summary of the samples taken between wall-clock times t0 and t1 (the sampler keeps running)."""
+    def window(self, t0, t1, gpus):
+        """Per-GPU clock summary (list indexed like `gpus`) of the samples taken between wall-clock times t0 and t1
+        (the sampler keeps running)."""
         if self.proc is None:
-            return None
+            return [None] * len(gpus)
         time.sleep(0.15)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except Exception:
-                continue
-            for nme, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        if not sm:
-            return None
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        out = []
+        for gidx in gpus:
+            sm, mx, pw, reasons = [], [], [], set()
+            for r in rows:
+                f = [x.strip() for x in r.split(",")]
+                try:
+                    if int(f[0]) != gidx:
+                        continue
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                    pw.append(float(f[3]))
+                except Exception:
+                    continue
+                for nme, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            out.append(dict(gpu=gidx, sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w=statistics.median(pw),
+                            reasons=sorted(reasons), samples=len(sm)) if sm else None)
+        return out
 
 
 def cpu_reference_rate(wl, frames, threads, repeats=1):
@@ -199,7 +207,7 @@ def build_quantizer(wl, dev, args):
     return quant
 
 
-def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, sampler=None):
+def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, settle=True):
     """W (+ clock-settling) untimed steps, then exactly `steps` timed steps bracketed by barrier + synchronize;
     device time = max over ranks.  Returns a dict of the raw numbers."""
     import torch
@@ -213,7 +221,7 @@ def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, sampler=None):
     # 1 / (1 - decay) = 100 steps, and the kernel's time depends on the codebooks (how many frames need the exact
     # re-rank): time the steady state, not that transient (profiles/r2b_c3_comm_probe_2gpu.log: the first 30 steps after
     # the statistics change scale run 5 % slower than the steady state)
-    n_warm = max(warmup, 150 if wl["update"] else 3)
+    n_warm = max(warmup, 150 if wl["update"] else 3) if settle else warmup
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0.record()
     out = None
@@ -225,6 +233,8 @@ def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, sampler=None):
     # handful of millisecond-long launches to reach its steady clocks).  The number of extra steps is agreed
     # across ranks (EMA workloads all-reduce every step); the timed region below is exactly K steps.
     extra = torch.tensor([max(0.0, 400.0 - w0.elapsed_time(w1)) / max(w0.elapsed_time(w1) / n_warm, 1e-3)], device=dev)
+    if not settle:
+        extra.zero_()
     if world > 1:
         dist.all_reduce(extra, op=dist.ReduceOp.MAX)
     for _ in range(min(int(extra.item()), 2000)):
@@ -250,11 +260,14 @@ def timed_steps(quant, x, wl, steps, warmup, rank, world, dev, sampler=None):
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.kernel_events)
     comm_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.comm_events) if quant.comm_events else 0.0
     upd_ms = statistics.mean(a.elapsed_time(b) for a, b in quant.update_events) if quant.update_events else 0.0
+    # device time between the end of the encode kernel and the start of the all-reduce (reseed gather, host launch gap)
+    pre_ms = (statistics.mean(u[0].elapsed_time(c[0]) for u, c in zip(quant.update_events, quant.comm_events))
+              if quant.comm_events and quant.update_events else 0.0)
     quant.kernel_events = quant.comm_events = quant.update_events = None
     ms = ms_local
     per_rank = None
     if world > 1:
-        t = torch.tensor([ms_local, kernel_ms, comm_ms, upd_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_local, kernel_ms, comm_ms, upd_ms, pre_ms], device=dev, dtype=torch.float64)
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         dist.barrier()
@@ -293,34 +306,35 @@ def collective_leg(args, rank, world, local, dev, sampler):
     steps = max(5, min(args.steps, 20))
     r = timed_steps(quant, x, wl, steps, args.warmup, rank, world, dev)
     parity = replicas_identical(quant, world, dev)
-    clocks = sampler.window(*r["wall"]) if sampler is not None else None
+    walls = [r["wall"]]
+    if world > 1:
+        walls = [None] * world
+        dist.all_gather_object(walls, r["wall"])
+    all_clocks = sampler.window(min(w[0] for w in walls), max(w[1] for w in walls), list(range(world))) if rank == 0 else None
     # the same step with the all-reduce skipped (every rank updates from its own shard): what this GPU does on
-    # its own while its neighbours are just as busy - the denominator of the collective's efficiency
+    # its own while its neighbours are just as busy - the denominator of the collective's efficiency.  Timed RIGHT
+    # AFTER the synchronised steps with three warm-up steps only: the encode kernel's time depends on the codebooks
+    # (profiles/r2b_c3_comm_probe_8gpu.log), and the two measurements must see the same ones.
     local_rate = local_kms = None
     if world > 1:
         quant.sync_stats = False
-        r0 = timed_steps(quant, x, wl, steps, args.warmup, rank, world, dev)
+        r0 = timed_steps(quant, x, wl, steps, 3, rank, world, dev, settle=False)
         quant.sync_stats = True
         local_rate = N * world * steps / (r0["ms"] * 1e-3)
         local_kms = [p[1] for p in r0["per_rank"]]
-    all_clocks = None
-    if world > 1:
-        all_clocks = [None] * world
-        dist.all_gather_object(all_clocks, clocks)
-    else:
-        all_clocks = [clocks]
     value = N * world * steps / (r["ms"] * 1e-3)
     flops_per_frame = nq * 2 * K * d
     peaks = load_peaks()
     kms = [p[1] for p in r["per_rank"]] if r["per_rank"] else [r["kernel_ms"]]
     cms = [p[2] for p in r["per_rank"]] if r["per_rank"] else [r["comm_ms"]]
     ums = [p[3] for p in r["per_rank"]] if r["per_rank"] else [r["upd_ms"]]
+    pms = [p[4] for p in r["per_rank"]] if r["per_rank"] else [0.0]
     ms_step = r["ms"] / steps
     out = dict(workload="c3", desc=wl["desc"], value=value, unit="frames/s", per_gpu_value=value / world,
                steps=steps, ms_per_step=ms_step, frames_per_gpu=N,
                kernel_ms_min=min(kms), kernel_ms_max=max(kms), kernel_ms_per_rank=kms,
                allreduce_ms=max(cms), allreduce_ms_per_rank=cms,
-               update_ms_per_rank=ums, k0_k3_ms=max(u - c for u, c in zip(ums, cms)),
+               update_ms_per_rank=ums, kernel_end_to_allreduce_start_ms_per_rank=pms, k0_k3_ms=max(u - c for u, c in zip(ums, cms)),
                k0_k3_note="CUDA events from the end of the encode kernel to the end of the codebook maintenance "
                           "(update_ms: all-reduce + rvq_ema_finalize K3 [+ SOM / re-seeding]); k0_k3_ms = that minus the "
                           "all-reduce; rvq_prepare_codebooks (K0) runs at the start of the next call, inside ms_per_step",
@@ -413,8 +427,9 @@ def run_c5(args, wl, rank, world, local, dev):
     g = torch.Generator(device=dev).manual_seed(77 + rank)
     B, T = 8, 240000
     x = torch.randn(B, 1, T, device=dev, generator=g) * 0.1
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
 
     def step():
         with torch.no_grad():
@@ -441,7 +456,7 @@ def run_c5(args, wl, rank, world, local, dev):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clocks = sampler.window(t0, t1)
+    clocks = sampler.window(t0, t1, list(range(world))) if rank == 0 else None
     sampler.stop()
     if rank == 0:
         out = dict(metric="rvq_frames_per_sec", value=frames * world * args.steps / (ms * 1e-3), unit="frames/s",
@@ -516,11 +531,15 @@ def main():
     # the clock sampler (nvidia-smi -lms) starts BEFORE the warm-up: its start-up (NVML initialisation) was seen to
     # stall kernel launches for tens of milliseconds when it fell into the timed region; rows are filtered by time.
     # One sampler per rank, each on its own GPU.
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
     r = timed_steps(quant, x, wl, args.steps, args.warmup, rank, world, dev)
     ms, kernel_ms, n_warm = r["ms"], r["kernel_ms"], r["n_warm"]
-    clocks = sampler.window(*r["wall"])
+    clocks = None
+    if rank == 0:
+        per_gpu = sampler.window(*r["wall"], list(range(world)))
+        clocks = dict(per_gpu[0] or {}, per_gpu=per_gpu) if per_gpu and per_gpu[0] else None
     frames_total = N * world * args.steps
     value = frames_total / (ms * 1e-3)
     ms_per_step = ms / args.steps

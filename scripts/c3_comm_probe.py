@@ -23,10 +23,25 @@ class A:
 wl = dict(bench.WORKLOADS["c3"])
 q = bench.build_quantizer(wl, dev, A)
 x = torch.randn(wl["frames"], wl["d"], device=dev)
-for name, sync, copy in [("no all-reduce", False, False), ("all-reduce in place", True, False), ("all-reduce on a copy", True, True),
-                         ("no all-reduce", False, False), ("all-reduce in place", True, False)]:
+tiny = torch.zeros(1, device=dev)
+orig_update = q._update_codebooks
+lockstep = [False]
+
+
+def update(*a, **k):
+    if lockstep[0]:                 # keeps the ranks in lockstep (4-byte all-reduce) without touching the statistics
+        dist.all_reduce(tiny)
+    return orig_update(*a, **k)
+
+
+q._update_codebooks = update
+WARM = int(os.environ.get("PROBE_WARM", "60"))
+for name, sync, copy, lock in [("no all-reduce", False, False, False), ("all-reduce in place", True, False, False),
+                               ("no all-reduce", False, False, False), ("4-byte all-reduce only (lockstep)", False, False, True),
+                               ("all-reduce on a copy", True, True, False), ("all-reduce in place", True, False, False)]:
     q.sync_stats, q.comm_copy = sync, copy
-    for _ in range(10):
+    lockstep[0] = lock
+    for _ in range(WARM):
         with torch.no_grad():
             q(x, None, update_codebook=True)
     torch.cuda.synchronize()
@@ -47,7 +62,7 @@ for name, sync, copy in [("no all-reduce", False, False), ("all-reduce in place"
     dist.all_gather(allt, t)
     q.kernel_events = q.comm_events = q.update_events = None
     if rank == 0:
-        print(f"{name:22s} world={world}: " + " | ".join(
+        print(f"{name:34s} world={world}: " + " | ".join(
             f"rank {i}: step {a[0]:.3f} kernel {a[1]:.3f} allreduce {a[2]:.3f} maintenance {a[3]:.3f} ms" for i, a in enumerate(allt)),
             flush=True)
 dist.destroy_process_group()
