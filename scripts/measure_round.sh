@@ -7,11 +7,12 @@ tag=${1:-r1c}
 out=gpurun_out
 mkdir -p $out
 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench_c2.json 2> $out/${tag}_bench.err
-RVQ_CLUSTER=1 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e > $out/${tag}_bench_c2_cluster1.json 2>> $out/${tag}_bench.err
+python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-collective --no-latency --kernel frame > $out/${tag}_bench_c2_frame_kernel.json 2>> $out/${tag}_bench.err
 python bench.py --workload c3 --steps 20 --warmup 5 --no-cpu > $out/${tag}_bench_c3.json 2>> $out/${tag}_bench.err
 python bench.py --workload c3m --steps 20 --warmup 5 --no-cpu > $out/${tag}_bench_c3m.json 2>> $out/${tag}_bench.err
 python bench.py --workload c4s --steps 5 --warmup 3 --no-cpu --no-e2e > $out/${tag}_bench_c4s.json 2>> $out/${tag}_bench.err
 python bench.py --workload c5q --steps 10 --warmup 3 --no-cpu --no-e2e > $out/${tag}_bench_c5q.json 2>> $out/${tag}_bench.err
+python bench.py --workload c5 --steps 5 --warmup 3 > $out/${tag}_bench_c5.json 2>> $out/${tag}_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference_cpu.json 2>> $out/${tag}_bench.err
 # launch list of the bench command (cold-cache, serialised: compare shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $out/${tag}_launches_c2.csv \
@@ -23,9 +24,9 @@ ncu --set full --import-source on --clock-control none -k regex:rvq_encode_tc --
     -o $out/${tag}_tc_c3_full -f python scripts/ncu_target.py c3 1048576 update > $out/${tag}_ncu_full_c3.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $out/${tag}_launches_c3.csv \
     python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu --no-e2e > $out/${tag}_ncu_launch_c3.log 2>&1
-for w in c2 c3; do RVQ_PROFILE=1 python scripts/phase_profile.py $w >> $out/${tag}_phase_profile.log 2>&1; done
+for w in c2 c3; do python scripts/phase_profile.py $w >> $out/${tag}_phase_profile.log 2>&1; done
 tail -2 $out/${tag}_bench.err
-for f in c2 c2_cluster1 c3 c3m c4s c5q reference_cpu; do python - <<PY
+for f in c2 c2_frame_kernel c3 c3m c4s c5q reference_cpu; do python - <<PY
 import json
 j = json.load(open("$out/${tag}_bench_$f.json"))
 r = j.get("roofline") or {}

@@ -1,8 +1,7 @@
-"""Per-phase cycle counters of the encode kernel (RVQ_PROFILE=1).  python scripts/phase_profile.py c2"""
+"""Per-phase cycle counters of the encode kernel (RVQ_FLAG_COUNTERS).  python scripts/phase_profile.py c2"""
 import os
 import sys
 
-os.environ["RVQ_PROFILE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
@@ -20,6 +19,7 @@ nsteps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv e
 with torch.no_grad():
     q.ema_sum.copy_(q.codebooks)
 q = q.cuda().train(upd)
+q.counters = True
 x = torch.randn(N, d, device="cuda")
 for _ in range(nsteps):
     with torch.no_grad():
@@ -39,13 +39,7 @@ ctas = min(148, (N + 127) // 128)
 cyc_total = ms * 1e-3 * 1.965e9 * ctas / n
 print(f"workload {name} update={upd} after {nsteps} steps N={N} ms={ms:.3f} tile-stages={prof[5]}  wall cycles per tile-stage per CTA ~{cyc_total:.0f} "
       f"(MMA floor {K * d * 128 // 4096})")
-if d <= 128 and os.environ.get("RVQ_KERNEL") != "tc" and os.environ.get("RVQ_SPEC", "0") != "0":
-    print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+a_ready wait {prof[1]/n:.0f}, of scan: tmem_full wait {prof[11]/n:.0f})")
-    print(f"  update group (per job, speculative order): total={prof[2]/n:.0f} (+scan_done wait {prof[7]/n:.0f})  classify[+fallback re-rank]={prof[8]/n:.0f} "
-          f"apply={prof[9]/n:.0f} verify+bookkeeping={prof[10]/n:.0f} tail={prof[12]/n:.0f}")
-    print(f"fallback-order jobs per job={prof[21]/n:.3f}  re-rank entries per tile-stage={prof[6]/n:.2f}  exact-scan frames per tile-stage={prof[4]/n:.3f}")
-    sys.exit(0)
-if d <= 128 and os.environ.get("RVQ_KERNEL") != "tc":
+if d <= 128:
     print(f"cycles per tile-stage: scan={prof[0]/n:.0f} (+a_ready wait {prof[1]/n:.0f}, of scan: tmem_full wait {prof[11]/n:.0f})")
     print(f"  update group (per job): total={prof[2]/n:.0f} (+scan_done wait {prof[7]/n:.0f})  staging-acquire={prof[3]/n:.0f} "
           f"rerank={prof[8]/n:.0f} gather-wait={prof[10]/n:.0f} apply={prof[9]/n:.0f} tail={prof[12]/n:.0f}")
