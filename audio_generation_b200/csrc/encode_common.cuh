@@ -38,9 +38,13 @@ __device__ __forceinline__ void row_consts(int d, float sq, bool force_exact, in
     // |approx - exact| (scaled units) <= 2^-9(1+..) rs cs  [fp16 rounding of both operands, Cauchy-Schwarz]
     //   + 2^-15 |score|                                   [slack for low mantissa bits used as tags]
     //   + d 2^-14                                          [fp16 subnormal absolute error, accumulate slack]
-    const float E = 1.02f * 0.001953125f * rs * cs + 3.0517578125e-5f * (na * cs * cs + 2.f * rs * cs) +
-                    (float)d * 6.103515625e-5f;
-    float delta = 2.1f * E;
+    const float mag = na * cs * cs + 2.f * rs * cs;  // >= |scaled score| and >= sum of |terms| of the exact scorer
+    const float E = 1.02f * 0.001953125f * rs * cs + 3.0517578125e-5f * mag + (float)d * 6.103515625e-5f;
+    // the exact fp32 scorer (exact.cuh: d/8 sequential fmaf per accumulator, 3 butterfly adds, one final fmaf) is
+    // itself within E32 = (d/8 + 4) 2^-24 mag of the real score; the winner under IT must stay inside best + delta:
+    //   s~(k^) <= best + 2 E + 2 E32          
+    const float E32 = (float)(d / 8 + 4) * 5.9604645e-8f * mag;
+    float delta = 2.1f * E + 2.f * E32;
     if (force_exact || !isfinite(delta)) delta = __int_as_float(0x7f800000);
     na_out = na;
     delta_out = delta;
