@@ -28,17 +28,8 @@
 namespace rvq {
 namespace tr {
 
-// RVQ_TR_A_TMEM (default): the fp16 operand A of the distance GEMM lives in TENSOR MEMORY (tcgen05.mma with A from
-// TMEM), 64 columns per tile slot, written by the frame's own update thread with tcgen05.st.  A 128 x 128 x 16 MMA
-// with both operands in shared memory reads 8 KiB per 64 cycles = 128 B/clk, the whole shared-memory bandwidth of the
-// SM: every other shared-memory access of the CTA (operand writes, staging, exposed rows, the TMA's own writes)
-// stretched the MMAs.  With A in TMEM only B crosses the shared-memory pipe (64 B/clk).  TMEM then holds
-// 2 x 64 accumulator columns + 2 x 64 operand columns + 2 x 128 residual columns = 512, hence 64-code accumulators.
-#ifndef RVQ_TR_A_TMEM
-#define RVQ_TR_A_TMEM 1
-#endif
 #ifndef RVQ_TR_CH
-#define RVQ_TR_CH (RVQ_TR_A_TMEM ? 64 : 128)
+#define RVQ_TR_CH 128
 #endif
 constexpr int CH = RVQ_TR_CH;  // codes per MMA / accumulator buffer (64 or 128)
 constexpr uint32_t NSLICE_BYTES = CH * 32;  // norm slice of one chunk
@@ -53,8 +44,6 @@ constexpr uint32_t B_STAGE_BYTES = CH * KSLICE * 2;  // 16 KiB
 constexpr uint32_t BAR_SCAN = 1;                     // named barrier of the 256 scan threads
 constexpr uint32_t BAR_GRP0 = 2;                     // + slot: named barrier of one update group
 constexpr uint32_t TMEM_RES_COL = 256;               // first residual column
-constexpr uint32_t TMEM_A_COL = 128;                 // first operand column (RVQ_TR_A_TMEM): slot s at + 64 s
-static_assert(!RVQ_TR_A_TMEM || CH == 64, "the operand columns [128, 256) need the accumulators inside [0, 128)");
 constexpr int RS_ROWS = 16;  // re-rank entries (residual row + four candidates) per round: 8 lanes per entry
 
 struct Params {
@@ -221,19 +210,10 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                             tc_fence_after_sync();
                             const uint64_t bdesc = bdesc0 + (uint64_t)(st * (B_STAGE_BYTES >> 4));
                             // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
-#if RVQ_TR_A_TMEM
-                            // 64 features = 32 operand columns per slice, 8 columns per K = 16 step
-                            const uint32_t ta = tmem_base + TMEM_A_COL + (uint32_t)sl * 64u + (uint32_t)ks * 32u;
-                            umma_f16_ts(tmem_d, ta, bdesc, idesc, ks != 0);
-                            umma_f16_ts(tmem_d, ta + 8, bdesc + 2, idesc, 1);
-                            umma_f16_ts(tmem_d, ta + 16, bdesc + 4, idesc, 1);
-                            umma_f16_ts(tmem_d, ta + 24, bdesc + 6, idesc, 1);
-#else
                             umma_f16_ss(tmem_d, adesc, bdesc, idesc, ks != 0);
                             umma_f16_ss(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
                             umma_f16_ss(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
                             umma_f16_ss(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
-#endif
                             // frees the ring slot (in every CTA of the cluster) when these MMAs retire
                             if (CL > 1)
                                 umma_commit_mc(&misc->empty[st], cmask);
@@ -352,7 +332,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
         const int gw = warp & 3;                  // warp inside the group
         if (s < nslots) {
             const uint32_t t_r = tmem_base + ((uint32_t)(gw * 32) << 16) + TMEM_RES_COL + (uint32_t)(s * d);
-            [[maybe_unused]] const uint32_t t_a = tmem_base + ((uint32_t)(gw * 32) << 16) + TMEM_A_COL + (uint32_t)(s * 64);
             float* stg_row = staging + (size_t)row * p.pitch;
             float* stg_warp = staging + (size_t)(gw * 32) * p.pitch;  // first staging row of this warp's frames
             uint8_t* a_tile = smem + (size_t)s * a_tile_bytes;
@@ -379,15 +358,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             };
             // 32 consecutive features (c0 .. c0+31, inside one 64-feature slice) of my frame -> fp16 operand
             auto store_a = [&](int c0, const uint32_t (&v)[32], float sa) {
-#if RVQ_TR_A_TMEM
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const __half2 h = __floats2half2_rn(__uint_as_float(v[2 * j]) * sa, __uint_as_float(v[2 * j + 1]) * sa);
-                    pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-                }
-                tmem_st_32x16(t_a + (uint32_t)(c0 >> 1), pk);
-#else
                 uint8_t* base = a_row + (uint32_t)(c0 >> 6) * A_SLICE_BYTES;
                 const uint32_t j0 = ((uint32_t)c0 >> 3) & 7u;
 #pragma unroll
@@ -404,7 +374,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     pk.w = *reinterpret_cast<const uint32_t*>(&h);
                     *reinterpret_cast<uint4*>(base + ((((j0 + (uint32_t)j) << 4)) ^ rx)) = pk;
                 }
-#endif
             };
             // operand row of the norm term for a frame whose operand exponents are a (row) and b (codes)
             constexpr int NORM_WINDOW_LO = -10;  // below: 2^(a-b-4) leaves the fp16 normal range -> exact scan
@@ -502,9 +471,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     tmem_ld_wait();
                     store_a(c0, v, sa);
                 }
-#if RVQ_TR_A_TMEM
-                tmem_st_wait();
-#endif
                 store_a_extra(a, b);
                 float na, delta;
                 row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
@@ -521,7 +487,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 acquire(ticket);
                 load_tile(blockIdx.x + ps * gridDim.x);
                 release();
-                tc_fence_before_sync();  // operand / residual columns written with tcgen05.st are visible to the MMA
                 mbar_arrive(&misc->a_ready[s]);
             }
             constexpr bool stats = kStats;
@@ -762,15 +727,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     }
                     tmem_st_32x16(t_r + c0, v);
                     if (write_a) {
-#if RVQ_TR_A_TMEM
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __half2 hh = __floats2half2_rn(__uint_as_float(v[2 * j]) * sa, __uint_as_float(v[2 * j + 1]) * sa);
-                            pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
-                        }
-                        tmem_st_32x8(t_a + (uint32_t)(c0 >> 1), pk);
-#else
                         uint8_t* base = a_row + (uint32_t)(c0 >> 6) * A_SLICE_BYTES;
                         const uint32_t j0 = ((uint32_t)c0 >> 3) & 7u;
 #pragma unroll
@@ -787,7 +743,6 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                             pk.w = *reinterpret_cast<const uint32_t*>(&hh);
                             *reinterpret_cast<uint4*>(base + ((((j0 + (uint32_t)j) << 4)) ^ rx)) = pk;
                         }
-#endif
                     }
                 };
                 if constexpr (kStats) {
@@ -851,8 +806,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 if (write_a) {
                     fence_proxy_async_smem();
                     if (staged) release();
-                    tc_fence_before_sync();  // operand / residual columns written with tcgen05.st are visible to the MMA
-                mbar_arrive(&misc->a_ready[s]);
+                    mbar_arrive(&misc->a_ready[s]);
                 } else {
                     // ---------------- last stage: xq = x - final residual, then the slot takes its next tile
                     const long long off = valid ? p.ad.row(n) : 0;
@@ -901,8 +855,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     if (next_i < n_local) {
                         load_tile(blockIdx.x + next_i * gridDim.x);
                         release();
-                        tc_fence_before_sync();  // operand / residual columns written with tcgen05.st are visible to the MMA
-                mbar_arrive(&misc->a_ready[s]);
+                        mbar_arrive(&misc->a_ready[s]);
                     } else {
                         release();
                     }
