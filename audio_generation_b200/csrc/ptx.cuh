@@ -2,6 +2,7 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld), proxy fences.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 
 namespace rvq {
@@ -49,8 +50,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+#ifdef RVQ_DEBUG_HANG
+// bring-up aid (-DRVQ_DEBUG_HANG): a wait that lasts longer than ~0.5 s names its barrier and traps
+#define RVQ_HANG_CHECK(bar, parity, t0)                                                                          \
+    if (clock64() - (t0) > 1000000000ll) {                                                                      \
+        printf("HANG block %d thread %d waits on smem barrier 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, \
+               smem_u32(bar), (unsigned)(parity));                                                              \
+        __trap();                                                                                                \
+    }
+#else
+#define RVQ_HANG_CHECK(bar, parity, t0)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    [[maybe_unused]] const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        RVQ_HANG_CHECK(bar, parity, t0)
     }
 }
 
@@ -100,6 +114,76 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {  // whole warp
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// ---- cta_group::2: two CTAs of a cluster (ranks 2i, 2i+1) drive their tensor cores with ONE instruction stream:
+// M = 256 (128 rows per CTA, each from its own shared memory / into its own tensor memory), the N rows of B split
+// half and half between the two CTAs' shared memory.  All tcgen05 instructions of a kernel carry the same cta_group.
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot) {  // one whole warp in EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier at the same offset in every CTA of cta_mask when the pair's MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+// 2-D tiled load into THIS CTA's shared memory whose completion bytes are counted on the mbarrier at the same offset
+// in the pair's even CTA (the peer bit of the barrier address is cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+// mbarrier arrive on the barrier at the same offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+// wait with acquire at cluster scope (the arrivals come from both CTAs of the pair)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    [[maybe_unused]] const long long t0 = clock64();
+    do {
+        RVQ_HANG_CHECK(bar, parity, t0)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+            : "memory");
+    } while (!ok);
 }
 
 // SWIZZLE_128B, K-major shared-memory matrix descriptor (8-row x 128-byte atoms, SBO = 1024 B).

@@ -66,10 +66,11 @@ struct Params {
 };
 
 struct __align__(16) Misc {
-    uint64_t full[MAX_RING], empty[MAX_RING], tmem_full[2], tmem_empty[2], norm_full[2], a_ready[2], scan_done[2];
+    uint64_t full[MAX_RING], empty[MAX_RING], tmem_full[2], tmem_empty[2], a_ready[2], scan_done[2];
     uint64_t stg_full[2], stg_free;
+    uint64_t rc_ready[2];  // paired mode: this CTA's row constants of a job are written (a_ready lives in the leader)
     // norm term as one extra K = 16 MMA step, no-swizzle K-major operands (8-row x 16-byte core matrices):
-    alignas(128) uint8_t nslice[2][4096];   // B: norm slices of the chunk in each accumulator buffer (bulk-copied)
+    // (B side: the chunk's norm slices ride in the ring stage of its last slice)
     alignas(128) uint8_t a_extra[2][4096];  // A: per tile slot, row = {2^(a-b+11), 2^(a-b+1), 2^(a-b-4), 2^14, 0...}
     uint32_t tmem_base;
     float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
@@ -93,9 +94,17 @@ struct __align__(16) Misc {
 
 // kStats: EMA statistics requested (compile-time so that each instantiation carries one apply path only: the
 // update threads are register-bound)
-template <bool kStats>
+// kPair: the two CTAs of a cluster drive their tensor cores as ONE cta_group::2 MMA (M = 256: 128 frames per CTA,
+// N = 128 codes split 64 / 64 between the CTAs' shared memory).  A 128 x 128 x 16 MMA whose operands both sit in
+// one CTA's shared memory reads 8 KiB per 64 cycles = the SM's whole 128 B/clk of shared-memory bandwidth, on top of
+// which the TMA writes the very same B bytes: 108 KiB per 128-code chunk, 864 cycles at best for 576 cycles of tensor
+// work.  Paired, every SM reads its A (4 KiB) and only its half of B (2 KiB) per MMA and receives only that half
+// from the TMA: 72 KiB per chunk = the 576 cycles.  The leader (even CTA) issues; the peer's frames take part through
+// cluster-scope mbarrier arrivals on the leader's barriers and multicast tcgen05.commit.
+template <bool kStats, bool kPair>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_n,
+                     const Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* smem_b = smem + p.off_B;
     float* staging = reinterpret_cast<float*>(smem + p.off_stg);
@@ -117,15 +126,16 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
     if (threadIdx.x == 0) {
         for (int i = 0; i < nstage; ++i) {
             mbar_init(&misc->full[i], 1);
-            mbar_init(&misc->empty[i], (uint32_t)CL);  // one tcgen05.commit arrive per CTA of the cluster
+            // one tcgen05.commit arrive per CTA of the cluster (paired: ONE multicast commit of the leader)
+            mbar_init(&misc->empty[i], kPair ? 1u : (uint32_t)CL);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&misc->tmem_full[i], 1);
-            mbar_init(&misc->tmem_empty[i], 4);  // one arrive per scan warp of the group
-            mbar_init(&misc->norm_full[i], 1);
-            mbar_init(&misc->a_ready[i], GRP_THREADS);
+            mbar_init(&misc->tmem_empty[i], kPair ? 8 : 4);  // one arrive per scan warp of the group (of both CTAs)
+            mbar_init(&misc->a_ready[i], kPair ? 2 * GRP_THREADS : GRP_THREADS);
             mbar_init(&misc->scan_done[i], SCAN_THREADS);
             mbar_init(&misc->stg_full[i], GRP_THREADS);
+            mbar_init(&misc->rc_ready[i], GRP_THREADS);
             misc->n_special[i] = 0;
             misc->n_dirty[i] = 0;
         }
@@ -135,8 +145,23 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
     }
     for (int i = threadIdx.x; i < 2 * 4096 / 16; i += NUM_THREADS)
         reinterpret_cast<uint4*>(&misc->a_extra[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_b);
-    if (warp == 2) tmem_alloc<512>(&misc->tmem_base);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_b);
+        if constexpr (kPair) tma_prefetch_desc(&tmap_n);
+    }
+    if (warp == 2) {
+        if constexpr (kPair)
+            tmem_alloc_pair<512>(&misc->tmem_base);
+        else
+            tmem_alloc<512>(&misc->tmem_base);
+    }
+#ifdef RVQ_DEBUG_HANG
+    if (threadIdx.x == 0 && blockIdx.x < 2)
+        printf("block %d barriers: full 0x%x empty 0x%x tmem_full 0x%x tmem_empty 0x%x a_ready 0x%x scan_done 0x%x "
+               "stg_full 0x%x stg_free 0x%x\n", (int)blockIdx.x, smem_u32(misc->full), smem_u32(misc->empty),
+               smem_u32(misc->tmem_full), smem_u32(misc->tmem_empty), smem_u32(misc->a_ready),
+               smem_u32(misc->scan_done), smem_u32(misc->stg_full), smem_u32(&misc->stg_free));
+#endif
     tc_fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // the peers' barriers are initialised before anything is multicast to them
@@ -148,23 +173,114 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
     // setmaxnreg is warpgroup-aligned: one instruction per warpgroup, before its warps split into roles.
     if (warp < SCAN_WARP0) {
         reg_dealloc<40>();
+        if (warp == 0 && kPair) {
+            // ======================================================= TMA producer, paired: MY half of every chunk
+            // (64 codes x d features + their norm slices) into MY shared memory, bytes counted on the LEADER's barrier
+            if (elect_one()) {
+                uint32_t st = 0, ph = 0;
+                const uint32_t stage_bytes = (uint32_t)n_ks * (B_STAGE_BYTES / 2) + NSLICE_BYTES / 2;
+                const int nq_prep = (int)p.cb_meta[4];  // stages prepared: the norm slices follow their norms
+                const int nrow_base = nq_prep * p.Kpad / 64;  // norm slices as rows of 256 bytes of the cb_norm buffer
+                for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+                    const int q_abs = p.q_begin + job.q;
+                    const int row0 = q_abs * p.Kpad + (int)crank * (CH / 2);
+                    const int nrow0 = nrow_base + q_abs * n_chunks * (int)(NSLICE_BYTES / 256) + (int)crank * (int)(NSLICE_BYTES / 512);
+                    for (int c = 0; c < n_chunks; ++c) {
+                        mbar_wait(&misc->empty[st], ph ^ 1);  // the pair's MMAs on this slot have retired
+                        if (crank == 0) mbar_arrive_expect_tx(&misc->full[st], 2u * stage_bytes);
+                        uint8_t* dst = smem_b + (size_t)st * stage_bytes;
+                        for (int ks = 0; ks < n_ks; ++ks)
+                            tma_load_2d_pair(dst + (size_t)ks * (B_STAGE_BYTES / 2), &tmap_b, &misc->full[st], ks * KSLICE,
+                                             row0 + c * CH);
+                        tma_load_2d_pair(dst + (size_t)n_ks * (B_STAGE_BYTES / 2), &tmap_n, &misc->full[st], 0,
+                                         nrow0 + c * (int)(NSLICE_BYTES / 256));
+                        if (++st == (uint32_t)nstage) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1 && kPair) {
+            // ======================================================= MMA issuer, paired: the leader CTA's elected thread
+            if (crank == 0 && elect_one()) {
+                const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, 2 * TILE_M, CH);
+                const uint32_t stage_bytes = (uint32_t)n_ks * (B_STAGE_BYTES / 2) + NSLICE_BYTES / 2;
+                const uint32_t smem_b_u32 = smem_u32(smem_b);
+                uint32_t g = 0, aphase = 0, st = 0, ph = 0;
+                long long t_aready = 0;
+                for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
+                    const int sl = job.slot % nslots;
+                    const long long tw = clock64();
+                    mbar_wait_cluster(&misc->a_ready[sl], (aphase >> sl) & 1);  // both CTAs' update groups
+                    t_aready += clock64() - tw;
+                    aphase ^= 1u << sl;
+                    tc_fence_after_sync();
+                    const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + (size_t)sl * a_tile_bytes));
+                    const uint64_t adesc_x = umma_desc_nosw(smem_u32(misc->a_extra[sl]), 128, 256);
+                    for (int c = 0; c < n_chunks; ++c, ++g) {
+                        const uint32_t buf = g & 1, use = g >> 1;
+                        mbar_wait_cluster(&misc->tmem_empty[buf], (use & 1) ^ 1);  // both CTAs' scan groups
+                        mbar_wait(&misc->full[st], ph);
+                        tc_fence_after_sync();
+                        const uint32_t tmem_d = tmem_base + buf * CH;
+                        const uint32_t sbase = smem_b_u32 + st * stage_bytes;
+                        uint64_t adesc = adesc0;
+                        for (int ks = 0; ks < n_ks; ++ks) {
+                            const uint64_t bdesc = umma_desc_sw128(sbase + (uint32_t)ks * (B_STAGE_BYTES / 2));
+                            umma_f16_ss_pair(tmem_d, adesc, bdesc, idesc, ks != 0);
+                            umma_f16_ss_pair(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
+                            umma_f16_ss_pair(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
+                            umma_f16_ss_pair(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
+                            adesc += (uint64_t)(A_SLICE_BYTES >> 4);
+                        }
+                        // the norm term: + A_extra . B_extra^T, my 64 codes' slices behind my half of the chunk
+                        umma_f16_ss_pair(tmem_d, adesc_x,
+                                         umma_desc_nosw(sbase + (uint32_t)n_ks * (B_STAGE_BYTES / 2), 128, 256), idesc, 1);
+                        umma_commit_pair_mc(&misc->empty[st], 3);        // both CTAs' ring slots
+                        umma_commit_pair_mc(&misc->tmem_full[buf], 3);   // both CTAs' scan groups
+                        if (++st == (uint32_t)nstage) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                }
+                if (p.prof) atomicAdd(p.prof + 18, (unsigned long long)t_aready);
+            }
+            __syncwarp();
+        }
+        if constexpr (!kPair) {
+        // ring stage = one 64-feature slice of a 128-code chunk (16 KiB) + room for the chunk's norm slices (4 KiB),
+        // which travel with the chunk's LAST slice: the MMA thread waits on ONE barrier per slice and issues nothing
+        // but MMAs and commits (round 1 had it issue the norm-slice copy and wait on a third barrier per chunk: ~150
+        // single-thread instructions, ~1.2 k cycles, per 576 cycles of tensor work)
+        const uint32_t stage_bytes = B_STAGE_BYTES + NSLICE_BYTES;
         if (warp == 0) {
-            // ======================================================= TMA producer (codebook slices)
+            // ======================================================= TMA producer (codebook slices + norm slices)
             if (elect_one()) {
                 uint32_t st = 0, ph = 0;
                 const uint32_t part_bytes = B_STAGE_BYTES / (uint32_t)CL;
                 const int part_rows = CH / CL;
+                const int nq_prep = (int)p.cb_meta[4];  // stages prepared: the norm slices follow their norms
+                const uint8_t* nbase = reinterpret_cast<const uint8_t*>(p.cb_norm + (size_t)nq_prep * p.Kpad);
                 for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
                     const int row0 = (p.q_begin + job.q) * p.Kpad + (int)crank * part_rows;
+                    const uint8_t* nsrc = nbase + (size_t)(p.q_begin + job.q) * n_chunks * NSLICE_BYTES;
                     for (int c = 0; c < n_chunks; ++c) {
                         for (int ks = 0; ks < n_ks; ++ks) {
+                            const bool last = ks == n_ks - 1;
                             mbar_wait(&misc->empty[st], ph ^ 1);  // every CTA of the cluster has consumed the slot
-                            mbar_arrive_expect_tx(&misc->full[st], B_STAGE_BYTES);
-                            uint8_t* dst = smem_b + (size_t)st * B_STAGE_BYTES + crank * part_bytes;
+                            mbar_arrive_expect_tx(&misc->full[st], B_STAGE_BYTES + (last ? NSLICE_BYTES : 0u));
+                            uint8_t* sbase = smem_b + (size_t)st * stage_bytes;
+                            uint8_t* dst = sbase + crank * part_bytes;
                             if (CL > 1)  // my 1/CL of the slice goes to every CTA of the cluster
                                 tma_load_2d_mc(dst, &tmap_b, &misc->full[st], ks * KSLICE, row0 + c * CH, cmask);
                             else
                                 tma_load_2d(dst, &tmap_b, &misc->full[st], ks * KSLICE, row0 + c * CH);
+                            if (last)
+                                bulk_load_1d(sbase + B_STAGE_BYTES, nsrc + (size_t)c * NSLICE_BYTES, NSLICE_BYTES,
+                                             &misc->full[st]);
                             if (++st == (uint32_t)nstage) {
                                 st = 0;
                                 ph ^= 1u;
@@ -181,8 +297,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             // per MMA (no divisions, no per-iteration warp syncs, descriptors advanced by additions).
             if (elect_one()) {
                 const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CH);
-                const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_b));
-                const int nq_prep = (int)p.cb_meta[4];  // stages prepared: the norm slices follow their norms
+                const uint32_t smem_b_u32 = smem_u32(smem_b);
                 uint32_t g = 0, aphase = 0, st = 0, ph = 0;
                 long long t_aready = 0;
                 for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
@@ -193,49 +308,43 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     aphase ^= 1u << sl;
                     tc_fence_after_sync();
                     const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + (size_t)sl * a_tile_bytes));
-                    const uint8_t* nsrc = reinterpret_cast<const uint8_t*>(p.cb_norm + (size_t)nq_prep * p.Kpad) +
-                                          (size_t)(p.q_begin + job.q) * n_chunks * NSLICE_BYTES;
                     const uint64_t adesc_x = umma_desc_nosw(smem_u32(misc->a_extra[sl]), 128, 256);
                     for (int c = 0; c < n_chunks; ++c, ++g) {
                         const uint32_t buf = g & 1, use = g >> 1;
-                        mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
-                        tc_fence_after_sync();
-                        // the scan group has released this buffer: its norm slice can be replaced as well
-                        mbar_arrive_expect_tx(&misc->norm_full[buf], NSLICE_BYTES);
-                        bulk_load_1d(misc->nslice[buf], nsrc + (size_t)c * NSLICE_BYTES, NSLICE_BYTES, &misc->norm_full[buf]);
+                        mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);  // the scan group has released this buffer
                         const uint32_t tmem_d = tmem_base + buf * CH;
                         uint64_t adesc = adesc0;
                         for (int ks = 0; ks < n_ks; ++ks) {
                             mbar_wait(&misc->full[st], ph);
                             tc_fence_after_sync();
-                            const uint64_t bdesc = bdesc0 + (uint64_t)(st * (B_STAGE_BYTES >> 4));
+                            const uint32_t sbase = smem_b_u32 + st * stage_bytes;
+                            const uint64_t bdesc = umma_desc_sw128(sbase);
                             // +32 bytes per K=16 step inside the 128-byte swizzle row (encoded >> 4)
                             umma_f16_ss(tmem_d, adesc, bdesc, idesc, ks != 0);
                             umma_f16_ss(tmem_d, adesc + 2, bdesc + 2, idesc, 1);
                             umma_f16_ss(tmem_d, adesc + 4, bdesc + 4, idesc, 1);
                             umma_f16_ss(tmem_d, adesc + 6, bdesc + 6, idesc, 1);
+                            if (ks == n_ks - 1)  // the norm term: + A_extra . B_extra^T (write_norm_slice, rvq_aux.cu)
+                                umma_f16_ss(tmem_d, adesc_x, umma_desc_nosw(sbase + B_STAGE_BYTES, 128, 256), idesc, 1);
                             // frees the ring slot (in every CTA of the cluster) when these MMAs retire
                             if (CL > 1)
                                 umma_commit_mc(&misc->empty[st], cmask);
                             else
                                 umma_commit(&misc->empty[st]);
+                            if (ks == n_ks - 1) umma_commit(&misc->tmem_full[buf]);
                             adesc += (uint64_t)(A_SLICE_BYTES >> 4);
                             if (++st == (uint32_t)nstage) {
                                 st = 0;
                                 ph ^= 1u;
                             }
                         }
-                        // the norm term: + A_extra . B_extra^T (see write_norm_slice in rvq_aux.cu)
-                        mbar_wait(&misc->norm_full[buf], use & 1);
-                        tc_fence_after_sync();
-                        umma_f16_ss(tmem_d, adesc_x, umma_desc_nosw(smem_u32(misc->nslice[buf]), 128, 256), idesc, 1);
-                        umma_commit(&misc->tmem_full[buf]);
                     }
                 }
                 if (p.prof) atomicAdd(p.prof + 18, (unsigned long long)t_aready);
             }
             __syncwarp();
         }
+        }  // !kPair
     } else if (warp < UPD_WARP0) {
         reg_dealloc<88>();
         // =========================================================== scan groups (argmin epilogue)
@@ -247,7 +356,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next(), jpar ^= 1u) {
             const int sl = job.slot % nslots;
             long long t0 = clock64();
-            mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);  // row constants of this job are visible
+            mbar_wait(kPair ? &misc->rc_ready[sl] : &misc->a_ready[sl], (aphase >> sl) & 1);  // row constants visible
             aphase ^= 1u << sl;
             const float delta = misc->row_delta[sl][my_row];
             float Cm[16];
@@ -277,7 +386,12 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 }
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&misc->tmem_empty[grp]);
+                if (lane == 0) {
+                    if constexpr (kPair)
+                        mbar_arrive_cluster(&misc->tmem_empty[grp], 0);  // the leader's barrier counts both CTAs
+                    else
+                        mbar_arrive(&misc->tmem_empty[grp]);
+                }
             }
             // ---------------- stage end: exchange the groups' best scores, list this group's candidates
             float vb_ = fminf(fminf(Cm[0], Cm[1]), Cm[2]);
@@ -487,7 +601,11 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 acquire(ticket);
                 load_tile(blockIdx.x + ps * gridDim.x);
                 release();
-                mbar_arrive(&misc->a_ready[s]);
+                if constexpr (kPair) {
+                    mbar_arrive(&misc->rc_ready[s]);            // my CTA's scan groups
+                    mbar_arrive_cluster(&misc->a_ready[s], 0);  // the leader issues the pair's MMAs
+                } else
+                    mbar_arrive(&misc->a_ready[s]);
             }
             constexpr bool stats = kStats;
             // a job takes a turn at the staging buffer only if it uses it: EMA statistics (the bulk reduction reads
@@ -806,6 +924,10 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 if (write_a) {
                     fence_proxy_async_smem();
                     if (staged) release();
+                    if constexpr (kPair) {
+                    mbar_arrive(&misc->rc_ready[s]);            // my CTA's scan groups
+                    mbar_arrive_cluster(&misc->a_ready[s], 0);  // the leader issues the pair's MMAs
+                } else
                     mbar_arrive(&misc->a_ready[s]);
                 } else {
                     // ---------------- last stage: xq = x - final residual, then the slot takes its next tile
@@ -855,7 +977,11 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                     if (next_i < n_local) {
                         load_tile(blockIdx.x + next_i * gridDim.x);
                         release();
-                        mbar_arrive(&misc->a_ready[s]);
+                        if constexpr (kPair) {
+                    mbar_arrive(&misc->rc_ready[s]);            // my CTA's scan groups
+                    mbar_arrive_cluster(&misc->a_ready[s], 0);  // the leader issues the pair's MMAs
+                } else
+                    mbar_arrive(&misc->a_ready[s]);
                     } else {
                         release();
                     }
@@ -899,7 +1025,10 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
     }
     if (warp == 2) {
         tc_fence_after_sync();
-        tmem_dealloc<512>(tmem_base);
+        if constexpr (kPair)
+            tmem_dealloc_pair<512>(tmem_base);
+        else
+            tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -951,20 +1080,28 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     p.nslots = 2;
     p.pitch = d + 4;
     const uint32_t a_bytes = (uint32_t)(d / KSLICE) * A_SLICE_BYTES;
+    // cluster: 0 / 1 = independent CTAs (default: fastest measured, profiles/r2d_*); 2 = the two CTAs of a cluster as
+    // ONE cta_group::2 MMA; 4 = independent tensor cores, one codebook stream multicast to four CTAs
+    const bool pair = cluster == 2;
+    const int CL = pair ? 2 : (cluster == 4 ? 4 : 1);
+    p.cluster = CL;
     const int stg_rows = TILE_M;  // staging buffer of one tile
     const uint32_t stg_bytes = (uint32_t)((stg_rows * p.pitch * 4 + 1023) / 1024 * 1024);
     const uint32_t misc_bytes = (uint32_t)((sizeof(tr::Misc) + 1023) / 1024 * 1024);
+    // ring stage: one 64-feature slice of a chunk; paired: MY half of a whole chunk (all slices + norm slices)
+    const uint32_t stage_bytes = pair ? (uint32_t)(d / KSLICE) * (tr::B_STAGE_BYTES / 2) + tr::NSLICE_BYTES / 2
+                                      : tr::B_STAGE_BYTES + tr::NSLICE_BYTES;
     p.off_stg = (uint32_t)p.nslots * a_bytes;
     p.off_B = p.off_stg + stg_bytes;
     const uint32_t fixed = p.off_B + misc_bytes + 1024;
-    int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / tr::B_STAGE_BYTES) : 0;
+    int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / stage_bytes) : 0;
     if (ns > tr::MAX_RING) ns = tr::MAX_RING;
     if (ns < 2) {
         set_error("rvq_encode: d=%d leaves no room for the codebook ring in %d bytes of shared memory", d, smem_max);
         return RVQ_ERR_ARG;
     }
     p.nstage = ns;
-    p.off_misc = p.off_B + (uint32_t)ns * tr::B_STAGE_BYTES;
+    p.off_misc = (p.off_B + (uint32_t)ns * stage_bytes + 1023u) / 1024u * 1024u;
     const uint32_t smem_total = p.off_misc + misc_bytes + 1024;
 
     EncodeTiledFn encode = get_encode_tiled_tr();
@@ -972,19 +1109,36 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
         set_error("rvq_encode: cuTensorMapEncodeTiled is not available from the driver");
         return RVQ_ERR_CUDA;
     }
-    CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nq_total * Kpad};
-    const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
-    const int CL = (cluster == 1 || cluster == 2 || cluster == 4) ? cluster : 2;
-    p.cluster = CL;
-    const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)(tr::CH / CL)};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(cb_op), gdim, gstride, box,
-                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        set_error("rvq_encode: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-        return RVQ_ERR_CUDA;
+    CUtensorMap tmap, tmap_n;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)nq_total * Kpad};
+        const cuuint64_t gstride[1] = {(cuuint64_t)d * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)KSLICE, (cuuint32_t)(tr::CH / (pair ? 2 : CL))};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(cb_op), gdim, gstride, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            set_error("rvq_encode: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+            return RVQ_ERR_CUDA;
+        }
+    }
+    {
+        // the cb_norm buffer as rows of 256 bytes: the paired producer fetches the norm slices of its 64 codes
+        // (2 KiB = 8 rows) with the tensor-map TMA, the only bulk copy that may complete on the peer CTA's mbarrier.
+        // The extent is a bound only: the buffer's real size (which depends on the number of prepared stages) is
+        // known to the device (cb_meta[4]), and no coordinate ever leaves it.
+        const cuuint64_t gdim[2] = {256, (cuuint64_t)1 << 24};
+        const cuuint64_t gstride[1] = {256};
+        const cuuint32_t box[2] = {256, (cuuint32_t)(tr::NSLICE_BYTES / 512)};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = encode(&tmap_n, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<float*>(cb_norm), gdim, gstride, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            set_error("rvq_encode: cuTensorMapEncodeTiled (norm slices) failed with CUresult %d", (int)cr);
+            return RVQ_ERR_CUDA;
+        }
     }
     const int num_tiles = (int)((N + TILE_M - 1) / TILE_M);
     p.x = x;
@@ -1005,7 +1159,8 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     p.stats_cnt = stats_cnt;
     p.num_tiles = num_tiles;
     p.prof = prof;  // 32 counters (RVQ_FLAG_COUNTERS) or null
-    auto kern = stats_sum ? tr::rvq_encode_tr_kernel<true> : tr::rvq_encode_tr_kernel<false>;
+    auto kern = stats_sum ? (pair ? tr::rvq_encode_tr_kernel<true, true> : tr::rvq_encode_tr_kernel<true, false>)
+                          : (pair ? tr::rvq_encode_tr_kernel<false, true> : tr::rvq_encode_tr_kernel<false, false>);
     RVQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_total));
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(tr::NUM_THREADS, 1, 1);
@@ -1030,7 +1185,7 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     const int want_clusters = (num_tiles + CL - 1) / CL;
     const int grid = (want_clusters < max_clusters ? want_clusters : max_clusters) * CL;
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    RVQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, p));
+    RVQ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, tmap_n, p));
     RVQ_CUDA(cudaGetLastError());
     return RVQ_OK;
 }

@@ -4,7 +4,8 @@ d = 64 / 128 / 256 runs `rvq_encode_fr_kernel` (thread = frame, residual residen
 into the MMA, cluster multicast of the codebook stream); other d, or kernel="generic", runs `rvq_encode_tc_kernel`;
 kernel="tmem" is round 1's kernel for d <= 128 (separate scan and update warps).  All of them use the same exact
 fp32 scorer for every frame the fp16 filter cannot certify, so on the same input they must return bit-identical code
-indices and outputs, whatever the cluster size.  The variants are selected through `flags` bits of `rvq_encode`
+indices and outputs, whatever the cluster size (for the "tmem" kernel cluster = 2 means the two CTAs of a cluster drive
+their tensor cores as ONE `tcgen05.mma.cta_group::2` instruction stream).  The variants are selected through `flags` bits of `rvq_encode`
 (include/rvq_sm100a.h), not through the environment.
 """
 import os
@@ -46,8 +47,8 @@ def test_kernels_agree_bitwise(d, K, N, strided):
     kw = dict(nq=5, K=K, d=d, N=N, strided=strided, update=False)
     a = run_variant("frame", 2, **kw)
     variants = [("frame", 1), ("frame", 4), ("generic", 0), ("generic", 2)]
-    if d <= 128:
-        variants += [("tmem", 1), ("tmem", 2)]
+    if d <= 128:   # independent CTAs (default), the cta_group::2 pair, one codebook stream multicast to four CTAs
+        variants += [("tmem", 1), ("tmem", 2), ("tmem", 4)]
     for kernel, cluster in variants:
         b = run_variant(kernel, cluster, **kw)
         name = f"{kernel}/{cluster}"
