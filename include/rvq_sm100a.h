@@ -46,7 +46,10 @@ typedef enum {
 #define RVQ_KERNEL_FRAME 0x20    /* rvq_encode_fr.cu: thread = frame, residual in tensor memory, d = 64 / 128 / 256 */
 #define RVQ_KERNEL_TMEM 0x30     /* rvq_encode_tr.cu: residual in tensor memory, scan and update warps, d = 64 / 128 */
 #define RVQ_FLAG_KERNEL_MASK 0xF0
-/* CTAs per cluster sharing one multicast codebook stream (bits 8-10): 0 = the kernel's default, else 1, 2 or 4 */
+/* CTAs per thread-block cluster (bits 8-10): 0 = the kernel's default (1: independent CTAs, the fastest measured),
+ * else 1, 2 or 4.  RVQ_KERNEL_TMEM: 2 = the two CTAs drive their tensor cores as ONE tcgen05.mma.cta_group::2
+ * instruction stream (B split between their shared memories), 4 = one codebook stream multicast to four CTAs;
+ * RVQ_KERNEL_FRAME / GENERIC: 2, 4 = multicast.  Results are bit-identical for every value. */
 #define RVQ_FLAG_CLUSTER_SHIFT 8
 #define RVQ_FLAG_CLUSTER_MASK 0x700
 /* event counters of the launch in the LAST 256 bytes of ws (uint64[32], zeroed by the call): test / profiling aid */
