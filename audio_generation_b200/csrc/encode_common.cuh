@@ -29,8 +29,9 @@ __device__ __forceinline__ uint32_t a_tile_offset(int row, int col) {
 // per-row constants of a stage from the residual's squared norm and the operand scales:
 //   na    = 2^(a-b): factor of the scaled code norms in this row's score unit
 //   delta = 2.1 x (proven bound on |approximate - exact| score), see DESIGN.md section 3
+//   rs    = 2^a ||r||_2 (upper bound): what the allowance of a code above the stage's norm cap is proportional to
 __device__ __forceinline__ void row_consts(int d, float sq, bool force_exact, int a, int b, float sb, float cnmax,
-                                           float& na_out, float& delta_out) {
+                                           float& na_out, float& delta_out, float& rs_out) {
     const float sa = exp2i(a);
     const float na = exp2i(max(-120, min(120, a - b)));
     const float rs = sqrtf(sq) * 1.00002f * sa;  // scaled ||r||_2 (upper bound)
@@ -48,6 +49,7 @@ __device__ __forceinline__ void row_consts(int d, float sq, bool force_exact, in
     if (force_exact || !isfinite(delta)) delta = __int_as_float(0x7f800000);
     na_out = na;
     delta_out = delta;
+    rs_out = isfinite(rs) ? rs : 0.f;
 }
 
 // operand scale exponent for a row whose entries are bounded by amax_bound, given the stage's b
@@ -78,9 +80,12 @@ constexpr uint32_t G_NOFILTER = 0x40000000u;  // no usable filter result at all 
 //     so {loads <= T} x {columns <= T} is a superset of the candidates: it is re-scored exactly.
 constexpr uint32_t IT_MASK = 0x1FFu;  // 32 chunks x 16 loads
 
-__device__ __forceinline__ void scan16_2d(const uint32_t (&v)[16], const float* __restrict__ nptr, float na,
-                                          uint32_t it, float (&Cm)[16], float& m1, float& m2, float& m3, float& m4,
-                                          float* dbg) {
+// kX: the chunk holds codes above the stage's norm cap: their allowance rs * xc_k (xptr, shared memory; nrs = -rs) is
+// subtracted (optimistic scores, see k0_bound in rvq_aux.cu); the na-proportional part X2_k is inside the stored norm
+template <bool kX>
+__device__ __forceinline__ void scan16_2d(const uint32_t (&v)[16], const float* __restrict__ nptr,
+                                          const float* __restrict__ xptr, float na, float nrs, uint32_t it,
+                                          float (&Cm)[16], float& m1, float& m2, float& m3, float& m4, float* dbg) {
     float s[16];
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
@@ -89,6 +94,13 @@ __device__ __forceinline__ void scan16_2d(const uint32_t (&v)[16], const float* 
         s[j + 1] = fmaf(na, nn.y, __uint_as_float(v[j + 1]));
         s[j + 2] = fmaf(na, nn.z, __uint_as_float(v[j + 2]));
         s[j + 3] = fmaf(na, nn.w, __uint_as_float(v[j + 3]));
+        if (kX) {
+            const float4 xx = *reinterpret_cast<const float4*>(xptr + j);
+            s[j + 0] = fmaf(nrs, xx.x, s[j + 0]);
+            s[j + 1] = fmaf(nrs, xx.y, s[j + 1]);
+            s[j + 2] = fmaf(nrs, xx.z, s[j + 2]);
+            s[j + 3] = fmaf(nrs, xx.w, s[j + 3]);
+        }
     }
     if (dbg) {
 #pragma unroll
@@ -108,6 +120,27 @@ __device__ __forceinline__ void scan16_2d(const uint32_t (&v)[16], const float* 
     const float w = fmaxf(m3, u);
     m3 = fminf(m3, u);
     m4 = fminf(m4, w);
+}
+
+// Allowance X of the code behind a frame's best (optimistic) score `vb` (k0_bound in rvq_aux.cu): the threshold is
+// T = vb + delta + 2 X.  The best score sits in column `jmin` (column minima are exact) of a load whose tagged minimum
+// lies within the tag's 2^-14 |vb| (x 1.016) of vb, i.e. of one of the three tracked loads unless a FOURTH load is that
+// close too - then the frame takes the exact scan anyway (that tolerance is inside T2 - vb >= 2^-13 |vb|) and the
+// stage maxima (xcmax, x2max) widen its threshold.  `xc`, `x2` point at the stage's per-code arrays.
+__device__ __forceinline__ float best_allowance(float vb, int jmin, float m1, float m2, float m3, float m4, float rs,
+                                                float na, const float* __restrict__ xc, const float* __restrict__ x2,
+                                                int kmax, float xcmax, float x2max) {
+    if (!(vb < BIG)) return 0.f;
+    const float lim = vb + fabsf(vb) * 6.2e-5f;
+    if (m4 <= lim) return rs * xcmax + na * x2max;
+    float x = 0.f;
+    const int k1 = min((int)((__float_as_uint(m1) & IT_MASK) * 16u) + jmin, kmax);
+    const int k2 = min((int)((__float_as_uint(m2) & IT_MASK) * 16u) + jmin, kmax);
+    const int k3 = min((int)((__float_as_uint(m3) & IT_MASK) * 16u) + jmin, kmax);
+    if (m1 <= lim) x = fmaxf(x, rs * __ldg(xc + k1) + na * __ldg(x2 + k1));
+    if (m2 <= lim) x = fmaxf(x, rs * __ldg(xc + k2) + na * __ldg(x2 + k2));
+    if (m3 <= lim) x = fmaxf(x, rs * __ldg(xc + k3) + na * __ldg(x2 + k3));
+    return x;
 }
 
 // same for accumulators that already contain the norm term (rvq_encode_tr.cu folds it into the MMA)

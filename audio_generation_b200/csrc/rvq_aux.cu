@@ -55,7 +55,7 @@ __global__ void k0_stage_max(const float* __restrict__ cb, const int* __restrict
 // {B1, B2, B3, PAD, 0...} with 2^11 B1 + 2 B2 + 2^-4 B3 = scaled norm exactly (three 11-bit pieces of the fp32
 // value) and PAD = 65504 for padding codes.  Stored per 128-code chunk in the canonical no-swizzle K-major UMMA
 // layout (8-row x 16-byte core matrices: row j, 16-byte K chunk kc at (j / 8) * 256 + kc * 128 + (j % 8) * 16).
-__device__ __forceinline__ void write_norm_slice(uint8_t* slices, int q, int Kpad, int k, float n, bool pad) {
+__device__ __forceinline__ void write_norm_slice(uint8_t* slices, int q, int Kpad, int k, float n, bool pad, float xc) {
     uint8_t* chunk = slices + ((size_t)q * (Kpad / 128) + k / 128) * 4096;
     const int j = k % 128;
     uint8_t* p0 = chunk + (j / 8) * 256 + (j % 8) * 16;
@@ -68,10 +68,14 @@ __device__ __forceinline__ void write_norm_slice(uint8_t* slices, int q, int Kpa
     }
     const __half2 a = __floats2half2_rn(h1 * 4.8828125e-4f, h2 * 0.5f);
     const __half2 b = __floats2half2_rn(h3 * 16.f, pad ? 65504.f : 0.f);
+    // fifth column: -(64 xc), rounded AWAY from zero (the operand row holds rs / 64 there, rounded up): the optimistic
+    // allowance rs * xc of a code whose norm exceeds the stage's cap (k0_bound)
+    const __half2 c = __halves2half2(__hneg(__float2half_ru(xc * 64.f)), __float2half_rn(0.f));
     uint4 v;
     v.x = *reinterpret_cast<const uint32_t*>(&a);
     v.y = *reinterpret_cast<const uint32_t*>(&b);
-    v.z = v.w = 0u;
+    v.z = *reinterpret_cast<const uint32_t*>(&c);
+    v.w = 0u;
     *reinterpret_cast<uint4*>(p0) = v;
     *reinterpret_cast<uint4*>(p0 + 128) = make_uint4(0u, 0u, 0u, 0u);
 }
@@ -88,10 +92,7 @@ __global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad
     __half* orow = op + ((size_t)q * Kpad + k) * d;
     if (k >= Kv) {
         for (int i = lane; i < d; i += 32) orow[i] = __float2half_rn(0.f);
-        if (lane == 0) {
-            norm[(size_t)q * Kpad + k] = PAD_NORM;
-            write_norm_slice(reinterpret_cast<uint8_t*>(norm + (size_t)nq * Kpad), q, Kpad, k, 0.f, true);
-        }
+        if (lane == 0) norm[(size_t)q * Kpad + k] = PAD_NORM;
         return;
     }
     const float* crow = cb + ((size_t)q * K + k) * d;
@@ -104,11 +105,94 @@ __global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad
     }
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     if (lane == 0) {
-        norm[(size_t)q * Kpad + k] = nrm * sb * sb;
-        write_norm_slice(reinterpret_cast<uint8_t*>(norm + (size_t)nq * Kpad), q, Kpad, k, nrm * sb * sb, false);
+        norm[(size_t)q * Kpad + k] = nrm * sb * sb;   // raw scaled norm; k0_bound finishes it
         // upper bound of ||c||_2 (fp32 summation slack) ; positive floats order like ints
         const float cn = sqrtf(nrm) * (1.f + 1e-5f);
         atomicMax(reinterpret_cast<int*>(mq + 1), __float_as_int(cn));
+    }
+}
+
+// Per-stage norm cap and the per-code allowances of the codes above it (one block per stage).
+//
+// The filter's error bound grows with the norm of the code.  A trained codebook holds a few codes
+// several times larger than the ones in use (dead codes that kept their initial scale): building the per-frame bound
+// from the LARGEST norm made the threshold 2-6x looser than the live codes need (profiles/r2e_c3_shards_probe.log).
+// Instead the stage gets a cap cs0 = min(max, 1.5 x the 25th percentile of the scaled norms); the frame's bound E0 is
+// built from cs0, and a code with cs_k > cs0 ("large") has its own excess X_k >= E_k + E32_k - (E0 + E32_0) SUBTRACTED
+// from its approximate score (an optimistic score v = s~ - X_k), which keeps the certificate rigorous:
+//     v(winner) <= v(j*) + 2 (E0 + E32_0) + 2 X_{j*}        for j* = argmin v        (derivation in DESIGN.md)
+// X_k = rs * xc_k + na * X2_k with  xc_k = c1 dcs_k,  X2_k = c2 (cs_k^2 - cs0^2),  dcs_k = cs_k - cs0,
+// c1 = alpha + 2 beta + 2 gamma,  c2 = beta + gamma  (row_consts); rs = 2^a ||r|| and na = 2^(a-b) belong to the frame.
+// X2_k is folded into the stored norm; rs * xc_k is one more rank-1 term of the extra MMA step (fifth norm-slice
+// column x rs in the operand row; TMEM kernels) or an FFMA in the epilogue of the chunks that hold a large code
+// (generic kernel: xc array, xflag per 256-code chunk).
+// The cap is the stage's lower-quartile norm (cs_max itself when the norms are concentrated, max <= 1.25 x quartile:
+// freshly initialised codebooks - no code is flagged and the generic kernel's epilogue stays on its short path).
+// Measured on C3 (profiles/r2g_probe_*.log): cap 1.5 x p25 14.66 / 15.41 ms (1 / 8 shards), p25 13.86 / 14.72,
+// the stage minimum 14.44 / 14.84.
+#ifndef RVQ_CAP_DIV
+#define RVQ_CAP_DIV 4
+#endif
+#ifndef RVQ_CAP_F
+#define RVQ_CAP_F 1.0f
+#endif
+#ifndef RVQ_CAP_FLAT
+#define RVQ_CAP_FLAT 1.25f
+#endif
+__global__ void __launch_bounds__(1024) k0_bound(float* __restrict__ norm, uint8_t* __restrict__ slices,
+                                                 float* __restrict__ xc, float* __restrict__ x2, int* __restrict__ xflag,
+                                                 float* __restrict__ meta, int Kpad, int d) {
+    const int q = blockIdx.x, t = threadIdx.x;
+    float* mq = meta + q * META_STRIDE;
+    const float sb = mq[0], cnmax = mq[1];
+    const int Kv = (int)mq[3];
+    __shared__ float samp[1024];
+    __shared__ float s_p25;
+    __shared__ int s_xcmax, s_x2max;
+    if (t == 0) s_xcmax = s_x2max = 0;
+    const int n = min(Kv, 1024);
+    const int stride = n > 0 ? Kv / n : 1;
+    if (t < n) samp[t] = sqrtf(norm[(size_t)q * Kpad + (size_t)t * stride]);
+    if (t == 0) s_p25 = 0.f;
+    __syncthreads();
+    if (t < n) {
+        const float mine = samp[t];
+        int rank = 0;
+        for (int u = 0; u < n; ++u) rank += (samp[u] < mine || (samp[u] == mine && u < t)) ? 1 : 0;
+        if (rank == n / RVQ_CAP_DIV) s_p25 = mine;
+    }
+    __syncthreads();
+    const float cs_max = cnmax * sb;
+    const float cs0 = (n > 0 && cs_max > RVQ_CAP_FLAT * s_p25) ? fminf(cs_max, RVQ_CAP_F * s_p25 * (1.f + 1e-5f)) : cs_max;
+    const float gamma = (float)(d / 8 + 4) * 5.9604645e-8f;
+    const float c1 = (1.02f * 0.001953125f + 2.f * 3.0517578125e-5f + 2.f * gamma) * 1.01f;
+    const float c2 = (3.0517578125e-5f + gamma) * 1.01f;
+    for (int k = t; k < Kpad; k += blockDim.x) {
+        const bool pad = k >= Kv;
+        const size_t i = (size_t)q * Kpad + k;
+        const float nk = norm[i];
+        const float csk = sqrtf(nk) * (1.f + 1e-5f);
+        const float dcs = (pad || !(csk > cs0)) ? 0.f : csk - cs0;
+        const float dcs2 = (pad || !(csk > cs0)) ? 0.f : csk * csk - cs0 * cs0;
+        const float XC = c1 * dcs, X2 = c2 * dcs2;
+        xc[i] = XC;
+        x2[i] = X2;
+        const float np = pad ? PAD_NORM : nk - X2;
+        norm[i] = np;
+        write_norm_slice(slices, q, Kpad, k, pad ? 0.f : np, pad, XC);
+        if (dcs > 0.f) {
+            // (non-negative floats order like ints: stage maxima; the flags are zeroed by the caller)
+            atomicOr(xflag + (size_t)q * (Kpad / CHUNK_N) + k / CHUNK_N, 1);
+            atomicMax(&s_xcmax, __float_as_int(XC));
+            atomicMax(&s_x2max, __float_as_int(X2));
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        mq[6] = cnmax;                       // the largest norm (diagnostics)
+        mq[1] = cs0 / sb;                    // what row_consts builds the frame's bound from
+        mq[7] = __int_as_float(s_xcmax);     // stage maxima of the allowances: frames that take the exact scan anyway
+        mq[5] = __int_as_float(s_x2max);
     }
 }
 
@@ -279,8 +363,9 @@ extern "C" int rvq_prepared_bytes(int nq, int K, int d, size_t* op_bytes, size_t
     }
     const size_t Kpad = round_up(K, CHUNK_N);
     if (op_bytes) *op_bytes = (size_t)nq * Kpad * d * sizeof(__half);
-    // scaled norms [nq, Kpad] fp32, then the fp16 norm slices [nq, Kpad / 128, 4096 bytes]
-    if (norm_bytes) *norm_bytes = (size_t)nq * Kpad * sizeof(float) + (size_t)nq * Kpad * 32;
+    // scaled norms [nq, Kpad] fp32, the fp16 norm slices [nq, Kpad / 128, 4096 bytes], the allowances of the codes
+    // above each stage's norm cap (two factors per code), per-chunk flags (NormLayout in common.cuh)
+    if (norm_bytes) *norm_bytes = NormLayout::bytes(nq, (int)Kpad);
     if (meta_bytes) *meta_bytes = (size_t)nq * META_STRIDE * sizeof(float);
     return RVQ_OK;
 }
@@ -309,6 +394,9 @@ extern "C" int rvq_prepare_codebooks(const float* cb, const int* k_valid, int nq
     const int block = 256;
     const long long grid = (warps * 32 + block - 1) / block;
     k0_convert<<<(unsigned)grid, block, 0, st>>>(cb, nq, K, Kpad, d, static_cast<__half*>(cb_op), cb_norm, cb_meta);
+    const NormLayout nl(cb_norm, nq, Kpad);
+    RVQ_CUDA(cudaMemsetAsync(nl.xflag, 0, sizeof(int) * (size_t)nq * (Kpad / CHUNK_N), st));
+    k0_bound<<<(unsigned)nq, 1024, 0, st>>>(cb_norm, nl.slices, nl.xc, nl.x2, nl.xflag, cb_meta, Kpad, d);
     RVQ_CUDA(cudaGetLastError());
     return RVQ_OK;
 }

@@ -414,8 +414,15 @@ rvq_encode_fr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             uint4 v;
             v.x = *reinterpret_cast<const uint32_t*>(&h01);
             v.y = *reinterpret_cast<const uint32_t*>(&h23);
-            v.z = v.w = 0u;
+            v.z = v.w = 0u;   // fifth column (rs / 64): store_a_rs, once the new residual's norm is known
             *reinterpret_cast<uint4*>(misc->a_extra[s] + (row >> 3) * 256 + (row & 7) * 16) = v;
+        };
+        // fifth operand column: rs / 64 rounded up, x (-64 xc_k) of the norm slice = the allowance rs * xc_k of the codes
+        // above the stage's norm cap (k0_bound in rvq_aux.cu)
+        auto store_a_rs = [&](float rs) {
+            const __half2 h45 = __halves2half2(__float2half_ru(rs * 0.015625f), __float2half_rn(0.f));
+            *reinterpret_cast<uint32_t*>(misc->a_extra[s] + (row >> 3) * 256 + (row & 7) * 16 + 8) =
+                *reinterpret_cast<const uint32_t*>(&h45);
         };
         // the warp's residual rows -> its scratch rows: lanes with `mine` store their row at scratch row `rank`
         auto expose_rows = [&](bool mine, int rank) {
@@ -435,7 +442,8 @@ rvq_encode_fr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
         };
 
         // per-frame state carried from the update of one stage to the scan of the next, in registers
-        float delta = 0.f, amax_bound = 0.f;
+        float delta = 0.f, amax_bound = 0.f, na_row = 1.f, rs_row = 0.f;
+        const NormLayout nl(p.cb_norm, (int)p.cb_meta[4], p.Kpad);
 
         // load tile `tile` into this slot: residual <- x, fp16 operand + row constants of the first stage
         auto load_tile = [&](int tile) {
@@ -508,8 +516,8 @@ rvq_encode_fr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                 store_a16(c0, v, sa);
             }
             store_a_extra(a, b);
-            float na;
-            row_consts(D, sq, force_exact, a, b, sb, cnmax, na, delta);
+            row_consts(D, sq, force_exact, a, b, sb, cnmax, na_row, delta, rs_row);
+            store_a_rs(rs_row);
             amax_bound = amax;
             fence_proxy_async_smem();
         };
@@ -589,11 +597,17 @@ rvq_encode_fr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             int jmin = 15;
 #pragma unroll
             for (int j = 14; j >= 0; --j) jmin = (Cm[j] == best) ? j : jmin;
-            // Certificate: a code can be the exact argmin only if its approximate score is <= T.
-            const float T = best + delta;
+            // allowance of the code behind the best score (zero unless it is above the stage's norm cap, k0_bound)
+            const float xbest = best_allowance(best, jmin, m1, m2, m3, m4, rs_row, na_row, nl.xc + (size_t)q_abs * p.Kpad,
+                                               nl.x2 + (size_t)q_abs * p.Kpad, p.Kpad - 1,
+                                               p.cb_meta[(size_t)q_abs * META_STRIDE + 7],
+                                               p.cb_meta[(size_t)q_abs * META_STRIDE + 5]);
+            // Certificate: a code can be the exact argmin only if its optimistic score is <= T.
+            const float dl = delta + 2.f * xbest;
+            const float T = best + dl;
             // load minima carry `it` in their low 9 mantissa bits: |packed - r| <= 2^-14 |r|, and every load
-            // minimum r of interest lies in [best, T], so |r| <= |best| + delta
-            const float T2 = T + (fabsf(best) + 2.f * delta) * 1.220703125e-4f;
+            // minimum r of interest lies in [best, T], so |r| <= |best| + dl
+            const float T2 = T + (fabsf(best) + 2.f * dl) * 1.220703125e-4f;
             // NaN / overflow / forced exact (no usable filter result), or more than three loads in reach
             const bool nofilter = !(best < BIG) || !(T2 < BIG);
             const bool over = nofilter || (m4 <= T2);
@@ -764,8 +778,8 @@ rvq_encode_fr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
             amax_bound = sqrtf(sq) * 1.00002f;  // ||r'||_2 >= max|r'|
             if (write_a) {
                 if (!isfinite(sq)) force_exact = true;
-                float na;
-                row_consts(D, sq, force_exact, a, b, sb, cnmax, na, delta);
+                row_consts(D, sq, force_exact, a, b, sb, cnmax, na_row, delta, rs_row);
+                store_a_rs(rs_row);
             }
             {
                 // commit-loss partial: sum over the valid frames of this warp

@@ -63,9 +63,11 @@ struct __align__(16) Misc {
     uint64_t full[MAX_STAGES_RING], empty[MAX_STAGES_RING], tmem_full[2], tmem_empty[2], a_ready[2], scan_done[2];
     uint64_t norm_full[2];
     alignas(16) float norms[2][CHUNK_N];  // scaled ||c||^2 of the chunk in each accumulator buffer (bulk-copied)
+    alignas(16) float xc[2][CHUNK_N];     // allowances XC_k of the chunk's codes above the norm cap (k0_bound)
+    float grp_x[2][2][TILE_M];            // [job parity][scan group][frame]: allowance of the group's best code
     uint32_t tmem_base;
     int dirty_count[2];
-    float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
+    float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M], row_rs[2][TILE_M];  // per tile slot
     float grp_best[2][2][TILE_M];            // [job parity][scan group][frame]: best score the group saw
     uint32_t g_rows[2][2][TILE_M];           // [slot][group][frame]: loads that may hold a candidate
     uint16_t g_cols[2][2][TILE_M];           // [slot][group][frame]: columns that may hold a candidate
@@ -90,10 +92,11 @@ struct RTile {
 // per-row constants of the next stage from the new residual's norm and the operand scale
 __device__ __forceinline__ void write_row_consts(const EncParams& p, Misc* misc, int sl, int row, int d, float sq,
                                                  bool force_exact, int a, int b, float sb, float cnmax) {
-    float na, delta;
-    row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
+    float na, delta, rs;
+    row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta, rs);
     misc->row_na[sl][row] = na;
     misc->row_delta[sl][row] = delta;
+    misc->row_rs[sl][row] = rs;
     if (p.dbg_rowscale) p.dbg_rowscale[row] = exp2i(a);
 }
 
@@ -422,6 +425,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_f16(0 /*fp16*/, TILE_M, CHUNK_N);
             const uint64_t bdesc0 = umma_desc_sw128(smem_u32(smem_b));
+            const int nq_prep = (int)p.cb_meta[4];  // stages prepared: locates the arrays behind the norms
             uint32_t g = 0, aphase = 0, st = 0, ph = 0;
             for (JobIter job(n_local, nq, nslots); job.valid(); job.next()) {
                 const int sl = job.slot % nslots;
@@ -430,13 +434,15 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 tc_fence_after_sync();
                 const uint64_t adesc0 = umma_desc_sw128(smem_u32(smem + (size_t)sl * a_tile_bytes));
                 const float* nsrc = p.cb_norm + (size_t)(p.q_begin + job.q) * p.Kpad;
+                const float* xsrc = NormLayout(p.cb_norm, nq_prep, p.Kpad).xc + (size_t)(p.q_begin + job.q) * p.Kpad;
                 for (int c = 0; c < n_chunks; ++c, ++g) {
                     const uint32_t buf = g & 1, use = g >> 1;
                     mbar_wait(&misc->tmem_empty[buf], (use & 1) ^ 1);
                     tc_fence_after_sync();
                     // the scan group has released this buffer: its norm slice can be replaced as well
-                    mbar_arrive_expect_tx(&misc->norm_full[buf], CHUNK_N * 4);
+                    mbar_arrive_expect_tx(&misc->norm_full[buf], 2 * CHUNK_N * 4);
                     bulk_load_1d(misc->norms[buf], nsrc + c * CHUNK_N, CHUNK_N * 4, &misc->norm_full[buf]);
+                    bulk_load_1d(misc->xc[buf], xsrc + c * CHUNK_N, CHUNK_N * 4, &misc->norm_full[buf]);
                     const uint32_t tmem_d = tmem_base + buf * CHUNK_N;
                     uint64_t adesc = adesc0;
                     for (int ks = 0; ks < n_ks; ++ks) {
@@ -473,14 +479,18 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
         uint32_t g = 0, aphase = 0, jpar = 0;
         long long t_scan = 0, t_wait = 0, t_full = 0;
+        const NormLayout nl(p.cb_norm, (int)p.cb_meta[4], p.Kpad);
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next(), jpar ^= 1u) {
             const int sl = job.slot % nslots;
             const int q_abs = p.q_begin + job.q;
+            const int* xflag = nl.xflag + (size_t)q_abs * n_chunks;
+            const float2 mq_x = make_float2(p.cb_meta[(size_t)q_abs * META_STRIDE + 7], p.cb_meta[(size_t)q_abs * META_STRIDE + 5]);
             long long t0 = clock64();
             mbar_wait(&misc->a_ready[sl], (aphase >> sl) & 1);  // row constants of this job are visible
             aphase ^= 1u << sl;
             const float na = misc->row_na[sl][my_row];
             const float delta = misc->row_delta[sl][my_row];
+            const float rs = misc->row_rs[sl][my_row];
             float Cm[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) Cm[j] = BIG;
@@ -496,6 +506,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 t_full += clock64() - tw0;
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * CHUNK_N;
                 const float* nptr = misc->norms[grp];
+                const float* xptr = misc->xc[grp];
+                const bool has_large = __ldg(xflag + c) != 0;  // warp-uniform: the chunk holds a code above the norm cap
                 float* dbg = nullptr;
                 if (kDebug && p.dbg_scores && job.i == 0 && job.q == 0)
                     dbg = p.dbg_scores + (size_t)my_row * p.Kpad + c * CHUNK_N;
@@ -504,15 +516,28 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 uint32_t va[16], vb[16];
                 tmem_ld_32x16(taddr, va);
                 uint32_t it = (uint32_t)c * (CHUNK_N / 16);
+                if (!has_large) {
 #pragma unroll 1
-                for (int cb = 0; cb < CHUNK_N; cb += 32, it += 2) {
-                    tmem_ld_wait();
-                    tmem_ld_32x16(taddr + cb + 16, vb);
-                    scan16_2d(va, nptr + cb, na, it, Cm, m1, m2, m3, m4, kDebug && dbg ? dbg + cb : nullptr);
-                    tmem_ld_wait();
-                    if (cb + 32 < CHUNK_N) tmem_ld_32x16(taddr + cb + 32, va);
-                    scan16_2d(vb, nptr + cb + 16, na, it + 1, Cm, m1, m2, m3, m4,
-                              kDebug && dbg ? dbg + cb + 16 : nullptr);
+                    for (int cb = 0; cb < CHUNK_N; cb += 32, it += 2) {
+                        tmem_ld_wait();
+                        tmem_ld_32x16(taddr + cb + 16, vb);
+                        scan16_2d<false>(va, nptr + cb, nullptr, na, 0.f, it, Cm, m1, m2, m3, m4, kDebug && dbg ? dbg + cb : nullptr);
+                        tmem_ld_wait();
+                        if (cb + 32 < CHUNK_N) tmem_ld_32x16(taddr + cb + 32, va);
+                        scan16_2d<false>(vb, nptr + cb + 16, nullptr, na, 0.f, it + 1, Cm, m1, m2, m3, m4,
+                                         kDebug && dbg ? dbg + cb + 16 : nullptr);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int cb = 0; cb < CHUNK_N; cb += 32, it += 2) {
+                        tmem_ld_wait();
+                        tmem_ld_32x16(taddr + cb + 16, vb);
+                        scan16_2d<true>(va, nptr + cb, xptr + cb, na, -rs, it, Cm, m1, m2, m3, m4, kDebug && dbg ? dbg + cb : nullptr);
+                        tmem_ld_wait();
+                        if (cb + 32 < CHUNK_N) tmem_ld_32x16(taddr + cb + 32, va);
+                        scan16_2d<true>(vb, nptr + cb + 16, xptr + cb + 16, na, -rs, it + 1, Cm, m1, m2, m3, m4,
+                                        kDebug && dbg ? dbg + cb + 16 : nullptr);
+                    }
                 }
                 tc_fence_before_sync();
                 __syncwarp();
@@ -524,14 +549,29 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             for (int j = 3; j < 15; j += 2) vb_ = fminf(fminf(vb_, Cm[j]), Cm[j + 1]);
             vb_ = fminf(vb_, Cm[15]);
             misc->grp_best[jpar][grp][my_row] = vb_;
+            // allowance of the code behind the group's best (optimistic) score: the threshold needs twice the
+            // allowance of the OVERALL best code (zero unless that code is above the stage's norm cap)
+            {
+                int jmin = 15;
+#pragma unroll
+                for (int j = 14; j >= 0; --j) jmin = (Cm[j] == vb_) ? j : jmin;
+                misc->grp_x[jpar][grp][my_row] =
+                    best_allowance(vb_, jmin, m1, m2, m3, m4, rs, na, nl.xc + (size_t)q_abs * p.Kpad,
+                                   nl.x2 + (size_t)q_abs * p.Kpad, p.Kpad - 1, mq_x.x, mq_x.y);
+            }
             named_bar_sync(BAR_SCAN, SCAN_THREADS);
             {
-                const float best = fminf(vb_, misc->grp_best[jpar][grp ^ 1][my_row]);
-                // Certificate: a code can be the exact argmin only if its approximate score is <= T.
-                const float T = best + delta;
+                const float ob = misc->grp_best[jpar][grp ^ 1][my_row];
+                const float best = fminf(vb_, ob);
+                const float xm = misc->grp_x[jpar][grp][my_row], xo = misc->grp_x[jpar][grp ^ 1][my_row];
+                const float tol = fabsf(best) * 6.2e-5f;
+                const float xbest = vb_ + tol < ob ? xm : (ob + tol < vb_ ? xo : fmaxf(xm, xo));
+                // Certificate: a code can be the exact argmin only if its optimistic score is <= T.
+                const float dl = delta + 2.f * xbest;
+                const float T = best + dl;
                 // load minima carry `it` in their low 9 mantissa bits: |packed - r| <= 2^-14 |r|, and every load
-                // minimum r of interest lies in [best, T], so |r| <= |best| + delta
-                const float T2 = T + (fabsf(best) + 2.f * delta) * 1.220703125e-4f;
+                // minimum r of interest lies in [best, T], so |r| <= |best| + dl
+                const float T2 = T + (fabsf(best) + 2.f * dl) * 1.220703125e-4f;
                 // NaN / overflow / forced exact (no usable filter result), or more than three loads in reach
                 const bool nofilter = !(best < BIG) || !(T2 < BIG);
                 const bool over = nofilter || (m4 <= T2);

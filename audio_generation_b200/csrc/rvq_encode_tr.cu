@@ -73,8 +73,9 @@ struct __align__(16) Misc {
     // (B side: the chunk's norm slices ride in the ring stage of its last slice)
     alignas(128) uint8_t a_extra[2][4096];  // A: per tile slot, row = {2^(a-b+11), 2^(a-b+1), 2^(a-b-4), 2^14, 0...}
     uint32_t tmem_base;
-    float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M];  // per tile slot
+    float row_na[2][TILE_M], row_delta[2][TILE_M], row_amax[2][TILE_M], row_rs[2][TILE_M];  // per tile slot
     float grp_best[2][2][TILE_M];   // [job parity][scan group][frame]: best score the group saw
+    float grp_x[2][2][TILE_M];      // [job parity][scan group][frame]: allowance of that score's code (k0_bound)
     uint16_t wbest[2][2][TILE_M];   // [slot][scan group][frame]: the code that scored it (approximate argmin)
     float vbest[2][2][TILE_M];      // [slot][scan group][frame]: that score
     // candidate sets, double buffered by stage parity: the verification of stage q may still read them while the
@@ -353,6 +354,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
         const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
         uint32_t g = 0, aphase = 0, jpar = 0;
         long long t_scan = 0, t_wait = 0, t_full = 0;
+        const NormLayout nl(p.cb_norm, (int)p.cb_meta[4], p.Kpad);
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next(), jpar ^= 1u) {
             const int sl = job.slot % nslots;
             long long t0 = clock64();
@@ -405,17 +407,29 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
                 int jmin = 15;
 #pragma unroll
                 for (int j = 14; j >= 0; --j) jmin = (Cm[j] == vb_) ? j : jmin;
-                misc->wbest[sl][grp][my_row] = (uint16_t)((__float_as_uint(m1) & IT_MASK) * 16u + (uint32_t)jmin);
+                const uint32_t kb = (__float_as_uint(m1) & IT_MASK) * 16u + (uint32_t)jmin;
+                misc->wbest[sl][grp][my_row] = (uint16_t)kb;
                 misc->vbest[sl][grp][my_row] = vb_;
+                // allowance of the code behind that score (zero unless it is above the stage's norm cap, k0_bound)
+                const int q_abs = p.q_begin + job.q;
+                misc->grp_x[jpar][grp][my_row] =
+                    best_allowance(vb_, jmin, m1, m2, m3, m4, misc->row_rs[sl][my_row], misc->row_na[sl][my_row],
+                                   nl.xc + (size_t)q_abs * p.Kpad, nl.x2 + (size_t)q_abs * p.Kpad, p.Kpad - 1,
+                                   p.cb_meta[(size_t)q_abs * META_STRIDE + 7], p.cb_meta[(size_t)q_abs * META_STRIDE + 5]);
             }
             named_bar_sync(BAR_SCAN, SCAN_THREADS);
             {
-                const float best = fminf(vb_, misc->grp_best[jpar][grp ^ 1][my_row]);
-                // Certificate: a code can be the exact argmin only if its approximate score is <= T.
-                const float T = best + delta;
+                const float ob = misc->grp_best[jpar][grp ^ 1][my_row];
+                const float best = fminf(vb_, ob);
+                const float xm = misc->grp_x[jpar][grp][my_row], xo = misc->grp_x[jpar][grp ^ 1][my_row];
+                const float tol = fabsf(best) * 6.2e-5f;
+                const float xbest = vb_ + tol < ob ? xm : (ob + tol < vb_ ? xo : fmaxf(xm, xo));
+                // Certificate: a code can be the exact argmin only if its optimistic score is <= T.
+                const float dl = delta + 2.f * xbest;
+                const float T = best + dl;
                 // load minima carry `it` in their low 9 mantissa bits: |packed - r| <= 2^-14 |r|, and every load
-                // minimum r of interest lies in [best, T], so |r| <= |best| + delta
-                const float T2 = T + (fabsf(best) + 2.f * delta) * 1.220703125e-4f;
+                // minimum r of interest lies in [best, T], so |r| <= |best| + dl
+                const float T2 = T + (fabsf(best) + 2.f * dl) * 1.220703125e-4f;
                 // NaN / overflow / forced exact (no usable filter result), or more than three loads in reach
                 const bool nofilter = !(best < BIG) || !(T2 < BIG);
                 const bool over = nofilter || (m4 <= T2);
@@ -498,8 +512,15 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
                 uint4 v;
                 v.x = *reinterpret_cast<const uint32_t*>(&h01);
                 v.y = *reinterpret_cast<const uint32_t*>(&h23);
-                v.z = v.w = 0u;
+                v.z = v.w = 0u;   // fifth column (rs / 64): store_a_rs, once the new residual's norm is known
                 *reinterpret_cast<uint4*>(misc->a_extra[s] + (row >> 3) * 256 + (row & 7) * 16) = v;
+            };
+            // fifth operand column: rs / 64 rounded up, x (-64 xc_k) of the norm slice = the allowance rs * xc_k of the
+            // codes above the stage's norm cap (k0_bound in rvq_aux.cu)
+            auto store_a_rs = [&](float rs) {
+                const __half2 h45 = __halves2half2(__float2half_ru(rs * 0.015625f), __float2half_rn(0.f));
+                *reinterpret_cast<uint32_t*>(misc->a_extra[s] + (row >> 3) * 256 + (row & 7) * 16 + 8) =
+                    *reinterpret_cast<const uint32_t*>(&h45);
             };
             // Coalesced asynchronous gather of one d-float row per frame of this warp into the staging buffer:
             // lane r's row number (index into `table`, rows of d floats; < 0 = none) is broadcast and the 32 lanes
@@ -586,11 +607,13 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
                     store_a(c0, v, sa);
                 }
                 store_a_extra(a, b);
-                float na, delta;
-                row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
+                float na, delta, rs;
+                row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta, rs);
+                store_a_rs(rs);
                 misc->row_amax[s][row] = amax;
                 misc->row_na[s][row] = na;
                 misc->row_delta[s][row] = delta;
+                misc->row_rs[s][row] = rs;
                 fence_proxy_async_smem();
             };
 
@@ -907,10 +930,12 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
                 misc->row_amax[s][row] = sqrtf(sq) * 1.00002f;  // ||r'||_2 >= max|r'|
                 if (write_a) {
                     if (!isfinite(sq)) force_exact = true;
-                    float na, delta;
-                    row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta);
+                    float na, delta, rs;
+                    row_consts(d, sq, force_exact, a, b, sb, cnmax, na, delta, rs);
+                    store_a_rs(rs);
                     misc->row_na[s][row] = na;
                     misc->row_delta[s][row] = delta;
+                    misc->row_rs[s][row] = rs;
                 }
                 {
                     // commit-loss partial: sum over the valid frames of this warp

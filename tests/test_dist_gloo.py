@@ -34,7 +34,8 @@ def _worker(rank, world, port, q, cls="ema"):
     flat = torch.zeros(nq * K * d + nq * K)
     flat[rank::world] = 1.0
     dist.all_reduce(flat)
-    q.put((rank, m.codebooks.detach().clone(), m.ema_count.clone(), idx.clone(), float(flat.sum())))
+    # numpy arrays travel by value (a tensor travels as a file descriptor the exiting worker may already have closed)
+    q.put((rank, m.codebooks.detach().numpy().copy(), m.ema_count.numpy().copy(), idx.numpy().copy(), float(flat.sum())))
     dist.destroy_process_group()
 
 
@@ -53,6 +54,7 @@ def test_sharded_update_equals_single_process(cls):
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    res = [(r, torch.from_numpy(cb), torch.from_numpy(cnt), torch.from_numpy(ix), tot) for r, cb, cnt, ix, tot in res]
     for p in procs:
         p.join(60)
     torch.manual_seed(7)

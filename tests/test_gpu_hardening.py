@@ -186,19 +186,25 @@ def test_certificate_survives_adversarial_inputs(d, kernel):
 # --------------------------------------------------------------------------------------------- (vi) the error bound
 @pytest.mark.parametrize("K,d", [(1024, 128), (1024, 256), (512, 512), (512, 64)])
 def test_proven_error_bound_holds_on_every_score(K, d):
-    """|approximate - exact| <= E for EVERY score the filter produces (here ~1e8 of them over
-    several input distributions), with E the bound the kernel derives its threshold delta = 2.1 E from:
-        E = 1.02 * 2^-9 * rs * cs + 2^-15 * (na * cs^2 + 2 rs cs) + d * 2^-14        (scaled units)
-    rs = 2^a ||r||, cs = 2^b max ||c||, na = 2^(a-b).  Measured through the bring-up hook of the generic kernel."""
+    """|approximate - exact| <= E_k for EVERY score the filter produces (~10^7 per shape, several
+    input distributions), E_k being the bound with the code's OWN norm
+        E_k = 1.02 * 2^-9 * rs * cs_k + 2^-15 * (na * cs_k^2 + 2 rs cs_k) + d * 2^-14        (scaled units)
+    rs = 2^a ||r||, cs_k = 2^b ||c_k||, na = 2^(a-b).  The frame's threshold is built from the stage's norm CAP cs0
+    (cb_meta[1]); codes above it have their allowance X_k = rs xc_k + na X2_k subtracted by the filter (optimistic scores),
+    so the hook returns v = s~ - X_k and the test checks |v + X_k - exact| <= E_k.  Measured through the bring-up hook of
+    the generic kernel; the "outliers" codebook makes sure codes above the cap exist."""
     from audio_generation_b200 import _lib
     from audio_generation_b200.quantizer import _ptr, _stream
     lib = _lib.load()
     Kpad = (K + 255) // 256 * 256
     g = torch.Generator(device="cuda").manual_seed(5)
     worst = 0.0
-    n_scores = 0
-    dists = ["gauss", "gauss_small", "uniform", "sparse", "cauchy", "aligned"]
+    n_scores = n_large = 0
+    dists = ["gauss", "gauss_small", "uniform", "sparse", "cauchy", "aligned", "outliers"]
     reps = max(1, int(1e8 / (len(dists) * 128 * K)) // 8)
+    gamma = (d // 8 + 4) * 2.0 ** -24
+    c1 = (1.02 * 2.0 ** -9 + 2 * 2.0 ** -15 + 2 * gamma) * 1.01
+    c2 = (2.0 ** -15 + gamma) * 1.01
     for dist in dists:
         m = quantizer(1, K, d)
         with torch.no_grad():
@@ -206,11 +212,22 @@ def test_proven_error_bound_holds_on_every_score(K, d):
                 m.codebooks.uniform_(-1, 1)
             elif dist == "sparse":
                 m.codebooks.mul_((torch.rand_like(m.codebooks) < 0.1).float())
+            elif dist == "outliers":          # a trained codebook: most codes small, a tenth kept their initial scale
+                m.codebooks.mul_(0.2)
+                m.codebooks[0, ::10] *= 20.0
         m = m.cuda()
         op, nrm, meta = m._prepared()
         sb = float(meta.reshape(1, 8)[0, 0])
-        cnmax = float(meta.reshape(1, 8)[0, 1])
+        cs0 = float(meta.reshape(1, 8)[0, 1]) * sb                      # the stage's norm cap (scaled)
         cb64 = m.codebooks[0].double()
+        csk = cb64.norm(dim=1) * sb * (1 + 1e-5)                        # [K]
+        large = csk > cs0
+        n_large += int(large.sum())
+        dcs = torch.where(large, csk - cs0, torch.zeros_like(csk))
+        dcs2 = torch.where(large, csk * csk - cs0 * cs0, torch.zeros_like(csk))
+        xc_dev = nrm[Kpad * 9: Kpad * 10][:K].double()                  # NormLayout: xc behind norms + slices
+        # (the device derives cs_k and the cap in fp32: codes barely above the cap differ in the last digits)
+        assert torch.allclose(xc_dev, c1 * dcs, rtol=1e-2, atol=c1 * cs0 * 1e-5)
         for rep in range(reps):
             x = torch.randn(128, d, device="cuda", generator=g)
             if dist == "gauss_small":
@@ -226,14 +243,21 @@ def test_proven_error_bound_holds_on_every_score(K, d):
             sa = rs_out.double()                                           # 2^a per frame
             exact = sa[:, None] * sb * ((cb64 * cb64).sum(1)[None, :] - 2.0 * x.double() @ cb64.t())
             rs = x.double().norm(dim=1) * 1.00002 * sa
-            cs = cnmax * sb
             na = sa / sb
-            E = 1.02 * 2.0 ** -9 * rs * cs + 2.0 ** -15 * (na * cs * cs + 2.0 * rs * cs) + d * 2.0 ** -14
-            ratio = ((scores[:, :K].double() - exact).abs() / E[:, None]).max()
+            Ek = (1.02 * 2.0 ** -9 * rs[:, None] * csk[None, :] +
+                  2.0 ** -15 * (na[:, None] * (csk * csk)[None, :] + 2.0 * rs[:, None] * csk[None, :]) + d * 2.0 ** -14)
+            Xk = rs[:, None] * xc_dev[None, :] + na[:, None] * (c2 * dcs2)[None, :]
+            ratio = ((scores[:, :K].double() + Xk - exact).abs() / Ek).max()
             worst = max(worst, float(ratio))
+            # and the allowance really covers what the own-norm bound exceeds the cap-based bound by
+            E0 = (1.02 * 2.0 ** -9 * rs * cs0 + 2.0 ** -15 * (na * cs0 * cs0 + 2.0 * rs * cs0) + d * 2.0 ** -14)
+            E32k = (d // 8 + 4) * 2.0 ** -24 * (na[:, None] * (csk * csk)[None, :] + 2.0 * rs[:, None] * csk[None, :])
+            E32_0 = (d // 8 + 4) * 2.0 ** -24 * (na * cs0 * cs0 + 2.0 * rs * cs0)
+            need = (Ek + E32k) - (E0 + E32_0)[:, None]
+            assert bool((Xk[:, large] >= need[:, large] - 1e-6 * E0[:, None]).all())
             n_scores += 128 * K
     assert worst < 1.0, worst
-    assert n_scores >= 1e7
+    assert n_scores >= 1e7 and n_large > 0
 
 
 # --------------------------------------------------------------------------------------------- autograd + maintenance
