@@ -25,22 +25,23 @@ constexpr float PAD_NORM = 1.2676506e30f;  // 2^100: padding codes can never be 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // Layout of the cb_norm buffer written by rvq_prepare_codebooks for `nq` prepared stages (floats unless noted):
-//   norm [nq, Kpad] | norm slices [nq, Kpad / 128, 4096 bytes] | xc [nq, Kpad] | x2 [nq, Kpad] | xflag int [nq, Kpad / 256]
-// xc, x2 = the two factors of the allowance X_k = rs xc_k + na x2_k of the codes above the stage's norm cap (k0_bound
-// in rvq_aux.cu); xflag = the 256-code chunk holds such a code.
+//   norm [nq, Kpad] | norm slices [nq, Kpad / 128, 4096 bytes] | xc [nq, Kpad] | xb bytes [nq, Kpad] | xflag int [nq, Kpad / 256]
+// Allowance X_k = rs xc_k + na x2_k of the codes above the stage's norm cap (k0_bound in rvq_aux.cu): xc = its first
+// factor (the second is folded into the norm), xb = one byte per code with X_k <= xb_k (rs U1 + na U2), U in the
+// stage's meta[7], meta[5]; xflag = the 256-code chunk holds such a code.
 struct NormLayout {
-    uint8_t* slices;
-    float *xc, *x2;
+    uint8_t *slices, *xb;
+    float* xc;
     int* xflag;
     __host__ __device__ NormLayout(const float* base, int nq, int Kpad) {
         float* b = const_cast<float*>(base);
         slices = reinterpret_cast<uint8_t*>(b + (size_t)nq * Kpad);
         xc = b + (size_t)nq * Kpad * 9;
-        x2 = b + (size_t)nq * Kpad * 10;
-        xflag = reinterpret_cast<int*>(b + (size_t)nq * Kpad * 11);
+        xb = reinterpret_cast<uint8_t*>(b + (size_t)nq * Kpad * 10);
+        xflag = reinterpret_cast<int*>(xb + (size_t)nq * Kpad);
     }
     static size_t bytes(int nq, int Kpad) {
-        return (size_t)nq * Kpad * 11 * sizeof(float) + (((size_t)nq * (Kpad / 256) * sizeof(int) + 15) & ~(size_t)15);
+        return (size_t)nq * Kpad * 41 + (((size_t)nq * (Kpad / 256) * sizeof(int) + 15) & ~(size_t)15);
     }
 };
 

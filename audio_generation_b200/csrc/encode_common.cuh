@@ -125,22 +125,20 @@ __device__ __forceinline__ void scan16_2d(const uint32_t (&v)[16], const float* 
 // Allowance X of the code behind a frame's best (optimistic) score `vb` (k0_bound in rvq_aux.cu): the threshold is
 // T = vb + delta + 2 X.  The best score sits in column `jmin` (column minima are exact) of a load whose tagged minimum
 // lies within the tag's 2^-14 |vb| (x 1.016) of vb, i.e. of one of the three tracked loads unless a FOURTH load is that
-// close too - then the frame takes the exact scan anyway (that tolerance is inside T2 - vb >= 2^-13 |vb|) and the
-// stage maxima (xcmax, x2max) widen its threshold.  `xc`, `x2` point at the stage's per-code arrays.
-__device__ __forceinline__ float best_allowance(float vb, int jmin, float m1, float m2, float m3, float m4, float rs,
-                                                float na, const float* __restrict__ xc, const float* __restrict__ x2,
-                                                int kmax, float xcmax, float x2max) {
-    if (!(vb < BIG)) return 0.f;
+// close too - then +inf comes back and the frame takes the exact scan of the whole stage.
+// `tab` = the stage's byte table (shared or global memory), xu = rs U1 + na U2 of this frame: X_k <= tab[k] * xu.
+__device__ __forceinline__ float best_allowance(float vb, int jmin, float m1, float m2, float m3, float m4, float xu,
+                                                const uint8_t* tab, int kmax) {
     const float lim = vb + fabsf(vb) * 6.2e-5f;
-    if (m4 <= lim) return rs * xcmax + na * x2max;
-    float x = 0.f;
-    const int k1 = min((int)((__float_as_uint(m1) & IT_MASK) * 16u) + jmin, kmax);
+    const int k1 = min((int)((__float_as_uint(m1) & IT_MASK) * 16u) + jmin, kmax);  // m1 <= lim always
     const int k2 = min((int)((__float_as_uint(m2) & IT_MASK) * 16u) + jmin, kmax);
     const int k3 = min((int)((__float_as_uint(m3) & IT_MASK) * 16u) + jmin, kmax);
-    if (m1 <= lim) x = fmaxf(x, rs * __ldg(xc + k1) + na * __ldg(x2 + k1));
-    if (m2 <= lim) x = fmaxf(x, rs * __ldg(xc + k2) + na * __ldg(x2 + k2));
-    if (m3 <= lim) x = fmaxf(x, rs * __ldg(xc + k3) + na * __ldg(x2 + k3));
-    return x;
+    // three independent loads, selected afterwards: one load latency on the stage's critical path
+    const uint32_t b1 = tab[k1], b2 = tab[k2], b3 = tab[k3];
+    const uint32_t b = max(b1, max(m2 <= lim ? b2 : 0u, m3 <= lim ? b3 : 0u));
+    float x = (float)b * xu;
+    x = (m4 <= lim) ? __int_as_float(0x7f800000) : x;
+    return (vb < BIG) ? x : 0.f;
 }
 
 // same for accumulators that already contain the norm term (rvq_encode_tr.cu folds it into the MMA)

@@ -140,7 +140,7 @@ __global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad
 #define RVQ_CAP_FLAT 1.25f
 #endif
 __global__ void __launch_bounds__(1024) k0_bound(float* __restrict__ norm, uint8_t* __restrict__ slices,
-                                                 float* __restrict__ xc, float* __restrict__ x2, int* __restrict__ xflag,
+                                                 float* __restrict__ xc, uint8_t* __restrict__ xb, int* __restrict__ xflag,
                                                  float* __restrict__ meta, int Kpad, int d) {
     const int q = blockIdx.x, t = threadIdx.x;
     float* mq = meta + q * META_STRIDE;
@@ -167,32 +167,55 @@ __global__ void __launch_bounds__(1024) k0_bound(float* __restrict__ norm, uint8
     const float gamma = (float)(d / 8 + 4) * 5.9604645e-8f;
     const float c1 = (1.02f * 0.001953125f + 2.f * 3.0517578125e-5f + 2.f * gamma) * 1.01f;
     const float c2 = (3.0517578125e-5f + gamma) * 1.01f;
+    // pass 1: stage maxima of the two allowance factors;  pass 2: everything that is stored
+    auto factors = [&](int k, float nk, float& XC, float& X2) {
+        const float csk = sqrtf(nk) * (1.f + 1e-5f);
+        const bool large = k < Kv && csk > cs0;
+        XC = large ? c1 * (csk - cs0) : 0.f;
+        X2 = large ? c2 * (csk * csk - cs0 * cs0) : 0.f;
+    };
+    {
+        float mxc = 0.f, mx2 = 0.f;
+        for (int k = t; k < Kpad; k += blockDim.x) {
+            float XC, X2;
+            factors(k, norm[(size_t)q * Kpad + k], XC, X2);
+            mxc = fmaxf(mxc, XC);
+            mx2 = fmaxf(mx2, X2);
+        }
+        // (non-negative floats order like ints)
+        if (mxc > 0.f) atomicMax(&s_xcmax, __float_as_int(mxc));
+        if (mx2 > 0.f) atomicMax(&s_x2max, __float_as_int(mx2));
+    }
+    __syncthreads();
+    // one byte per code: X_k <= xb_k (rs U1 + na U2) with U = stage maximum / 255 (what the kernels look up for the
+    // code behind a frame's best score: shared-memory table in the TMEM kernel)
+    const float U1 = __int_as_float(s_xcmax) * (1.f / 255.f) * (1.f + 2e-6f);
+    const float U2 = __int_as_float(s_x2max) * (1.f / 255.f) * (1.f + 2e-6f);
     for (int k = t; k < Kpad; k += blockDim.x) {
         const bool pad = k >= Kv;
         const size_t i = (size_t)q * Kpad + k;
         const float nk = norm[i];
-        const float csk = sqrtf(nk) * (1.f + 1e-5f);
-        const float dcs = (pad || !(csk > cs0)) ? 0.f : csk - cs0;
-        const float dcs2 = (pad || !(csk > cs0)) ? 0.f : csk * csk - cs0 * cs0;
-        const float XC = c1 * dcs, X2 = c2 * dcs2;
+        float XC, X2;
+        factors(k, nk, XC, X2);
         xc[i] = XC;
-        x2[i] = X2;
+        int bq = 0;
+        if (XC > 0.f) {
+            bq = (int)ceilf(XC / U1);
+            if (U2 > 0.f) bq = max(bq, (int)ceilf(X2 / U2));
+            while (bq < 255 && ((float)bq * U1 < XC || (float)bq * U2 < X2)) ++bq;
+            bq = min(max(bq, 1), 255);
+            atomicOr(xflag + (size_t)q * (Kpad / CHUNK_N) + k / CHUNK_N, 1);  // (zeroed by the caller)
+        }
+        xb[i] = (uint8_t)bq;
         const float np = pad ? PAD_NORM : nk - X2;
         norm[i] = np;
         write_norm_slice(slices, q, Kpad, k, pad ? 0.f : np, pad, XC);
-        if (dcs > 0.f) {
-            // (non-negative floats order like ints: stage maxima; the flags are zeroed by the caller)
-            atomicOr(xflag + (size_t)q * (Kpad / CHUNK_N) + k / CHUNK_N, 1);
-            atomicMax(&s_xcmax, __float_as_int(XC));
-            atomicMax(&s_x2max, __float_as_int(X2));
-        }
     }
-    __syncthreads();
     if (t == 0) {
-        mq[6] = cnmax;                       // the largest norm (diagnostics)
-        mq[1] = cs0 / sb;                    // what row_consts builds the frame's bound from
-        mq[7] = __int_as_float(s_xcmax);     // stage maxima of the allowances: frames that take the exact scan anyway
-        mq[5] = __int_as_float(s_x2max);
+        mq[6] = cnmax;      // the largest norm (diagnostics)
+        mq[1] = cs0 / sb;   // what row_consts builds the frame's bound from
+        mq[7] = U1;         // units of the byte table
+        mq[5] = U2;
     }
 }
 
@@ -364,7 +387,7 @@ extern "C" int rvq_prepared_bytes(int nq, int K, int d, size_t* op_bytes, size_t
     const size_t Kpad = round_up(K, CHUNK_N);
     if (op_bytes) *op_bytes = (size_t)nq * Kpad * d * sizeof(__half);
     // scaled norms [nq, Kpad] fp32, the fp16 norm slices [nq, Kpad / 128, 4096 bytes], the allowances of the codes
-    // above each stage's norm cap (two factors per code), per-chunk flags (NormLayout in common.cuh)
+    // above each stage's norm cap (xc per code, a byte table of the whole allowance), per-chunk flags (NormLayout)
     if (norm_bytes) *norm_bytes = NormLayout::bytes(nq, (int)Kpad);
     if (meta_bytes) *meta_bytes = (size_t)nq * META_STRIDE * sizeof(float);
     return RVQ_OK;
@@ -396,7 +419,7 @@ extern "C" int rvq_prepare_codebooks(const float* cb, const int* k_valid, int nq
     k0_convert<<<(unsigned)grid, block, 0, st>>>(cb, nq, K, Kpad, d, static_cast<__half*>(cb_op), cb_norm, cb_meta);
     const NormLayout nl(cb_norm, nq, Kpad);
     RVQ_CUDA(cudaMemsetAsync(nl.xflag, 0, sizeof(int) * (size_t)nq * (Kpad / CHUNK_N), st));
-    k0_bound<<<(unsigned)nq, 1024, 0, st>>>(cb_norm, nl.slices, nl.xc, nl.x2, nl.xflag, cb_meta, Kpad, d);
+    k0_bound<<<(unsigned)nq, 1024, 0, st>>>(cb_norm, nl.slices, nl.xc, nl.xb, nl.xflag, cb_meta, Kpad, d);
     RVQ_CUDA(cudaGetLastError());
     return RVQ_OK;
 }

@@ -598,10 +598,10 @@ rvq_encode_fr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
 #pragma unroll
             for (int j = 14; j >= 0; --j) jmin = (Cm[j] == best) ? j : jmin;
             // allowance of the code behind the best score (zero unless it is above the stage's norm cap, k0_bound)
-            const float xbest = best_allowance(best, jmin, m1, m2, m3, m4, rs_row, na_row, nl.xc + (size_t)q_abs * p.Kpad,
-                                               nl.x2 + (size_t)q_abs * p.Kpad, p.Kpad - 1,
-                                               p.cb_meta[(size_t)q_abs * META_STRIDE + 7],
-                                               p.cb_meta[(size_t)q_abs * META_STRIDE + 5]);
+            const float xbest = best_allowance(best, jmin, m1, m2, m3, m4,
+                                               fmaf(rs_row, p.cb_meta[(size_t)q_abs * META_STRIDE + 7],
+                                                    na_row * p.cb_meta[(size_t)q_abs * META_STRIDE + 5]),
+                                               nl.xb + (size_t)q_abs * p.Kpad, p.Kpad - 1);
             // Certificate: a code can be the exact argmin only if its optimistic score is <= T.
             const float dl = delta + 2.f * xbest;
             const float T = best + dl;

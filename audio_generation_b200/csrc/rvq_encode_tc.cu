@@ -556,8 +556,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
 #pragma unroll
                 for (int j = 14; j >= 0; --j) jmin = (Cm[j] == vb_) ? j : jmin;
                 misc->grp_x[jpar][grp][my_row] =
-                    best_allowance(vb_, jmin, m1, m2, m3, m4, rs, na, nl.xc + (size_t)q_abs * p.Kpad,
-                                   nl.x2 + (size_t)q_abs * p.Kpad, p.Kpad - 1, mq_x.x, mq_x.y);
+                    best_allowance(vb_, jmin, m1, m2, m3, m4, fmaf(rs, mq_x.x, na * mq_x.y),
+                                   nl.xb + (size_t)q_abs * p.Kpad, p.Kpad - 1);
             }
             named_bar_sync(BAR_SCAN, SCAN_THREADS);
             {

@@ -62,6 +62,7 @@ struct Params {
     int num_tiles, nstage, nslots, pitch;  // pitch: floats per staging row (d + 4)
     int cluster;                           // CTAs per cluster sharing the codebook stream (TMA multicast)
     uint32_t off_stg, off_B, off_misc;  // A tiles (one per slot) at offset 0
+    uint32_t off_tab;                   // two allowance byte tables of Kpad bytes each (0: looked up in global memory)
     unsigned long long* prof;              // [16] cycle / event counters (RVQ_PROFILE=1) or null
 };
 
@@ -90,6 +91,7 @@ struct __align__(16) Misc {
     float red_s[2][4];
     int red_k[2][4];
     double commit_acc[MAX_NQ];
+    float2 stage_u[MAX_NQ];  // units of the allowance byte table per stage (meta[7], meta[5]; k0_bound)
 };
 
 
@@ -146,6 +148,17 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
     }
     for (int i = threadIdx.x; i < 2 * 4096 / 16; i += NUM_THREADS)
         reinterpret_cast<uint4*>(&misc->a_extra[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < nq; i += NUM_THREADS) {
+        const float* mq = p.cb_meta + (size_t)(p.q_begin + i) * META_STRIDE;
+        misc->stage_u[i] = make_float2(mq[7], mq[5]);
+    }
+    // allowance byte table of the first stage (the scan threads keep the next stage's table one step ahead)
+    uint8_t* xtab = smem + p.off_tab;
+    if (p.off_tab) {
+        const NormLayout nl0(p.cb_norm, (int)p.cb_meta[4], p.Kpad);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(nl0.xb + (size_t)p.q_begin * p.Kpad);
+        for (int i = threadIdx.x; i < p.Kpad / 4; i += NUM_THREADS) reinterpret_cast<uint32_t*>(xtab)[i] = __ldg(src + i);
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_b);
         if constexpr (kPair) tma_prefetch_desc(&tmap_n);
@@ -352,12 +365,23 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
         const int e = threadIdx.x - SCAN_WARP0 * 32;  // 0..255
         const int grp = e >> 7;                       // scan group = accumulator buffer
         const int my_row = (warp & 3) * 32 + lane;    // TMEM lane owned by this thread
-        uint32_t g = 0, aphase = 0, jpar = 0;
+        uint32_t g = 0, aphase = 0, jpar = 0, step = 0;
         long long t_scan = 0, t_wait = 0, t_full = 0;
         const NormLayout nl(p.cb_norm, (int)p.cb_meta[4], p.Kpad);
+        const int tab_words = p.Kpad / 4;
         for (JobIter job(n_local, nq, nslots); job.valid(); job.next(), jpar ^= 1u) {
             const int sl = job.slot % nslots;
             long long t0 = clock64();
+            // Both slots run the same stage in consecutive jobs ("step").  The first job of a step copies the NEXT
+            // step's byte table into the other buffer: every reader of that buffer's old content (step - 1) is past
+            // the scan barrier that ended step - 1, and the scan barrier of this job orders the copy before the first
+            // lookup of the next step.  The word is loaded here and stored after the scan.
+            const bool tab_copy = p.off_tab != 0 && job.slot == 0;
+            step += job.slot == 0 ? 1u : 0u;
+            const uint32_t* tab_src = reinterpret_cast<const uint32_t*>(
+                nl.xb + (size_t)(p.q_begin + (job.q + 1 == nq ? 0 : job.q + 1)) * p.Kpad);
+            uint32_t tab_w = 0;
+            if (tab_copy && e < tab_words) tab_w = __ldg(tab_src + e);
             mbar_wait(kPair ? &misc->rc_ready[sl] : &misc->a_ready[sl], (aphase >> sl) & 1);  // row constants visible
             aphase ^= 1u << sl;
             const float delta = misc->row_delta[sl][my_row];
@@ -401,6 +425,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
             for (int j = 3; j < 15; j += 2) vb_ = fminf(fminf(vb_, Cm[j]), Cm[j + 1]);
             vb_ = fminf(vb_, Cm[15]);
             misc->grp_best[jpar][grp][my_row] = vb_;
+            float xm;
             {
                 // the code behind the group's best score: the load of the smallest load minimum, the first column
                 // that attains the column minimum
@@ -411,17 +436,25 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
                 misc->wbest[sl][grp][my_row] = (uint16_t)kb;
                 misc->vbest[sl][grp][my_row] = vb_;
                 // allowance of the code behind that score (zero unless it is above the stage's norm cap, k0_bound)
-                const int q_abs = p.q_begin + job.q;
-                misc->grp_x[jpar][grp][my_row] =
-                    best_allowance(vb_, jmin, m1, m2, m3, m4, misc->row_rs[sl][my_row], misc->row_na[sl][my_row],
-                                   nl.xc + (size_t)q_abs * p.Kpad, nl.x2 + (size_t)q_abs * p.Kpad, p.Kpad - 1,
-                                   p.cb_meta[(size_t)q_abs * META_STRIDE + 7], p.cb_meta[(size_t)q_abs * META_STRIDE + 5]);
+                const float2 u = misc->stage_u[job.q];
+                const float xu = fmaf(misc->row_rs[sl][my_row], u.x, misc->row_na[sl][my_row] * u.y);
+                // (two call sites: the shared-memory one compiles to LDS instead of generic loads)
+                xm = p.off_tab ? best_allowance(vb_, jmin, m1, m2, m3, m4, xu, xtab + ((step & 1u) ^ 1u) * (uint32_t)p.Kpad,
+                                                p.Kpad - 1)
+                               : best_allowance(vb_, jmin, m1, m2, m3, m4, xu,
+                                                nl.xb + (size_t)(p.q_begin + job.q) * p.Kpad, p.Kpad - 1);
+                misc->grp_x[jpar][grp][my_row] = xm;
+                if (tab_copy) {
+                    uint32_t* dst = reinterpret_cast<uint32_t*>(xtab + (step & 1u) * (uint32_t)p.Kpad);
+                    if (e < tab_words) dst[e] = tab_w;
+                    for (int w = e + 2 * GRP_THREADS; w < tab_words; w += 2 * GRP_THREADS) dst[w] = __ldg(tab_src + w);
+                }
             }
             named_bar_sync(BAR_SCAN, SCAN_THREADS);
             {
                 const float ob = misc->grp_best[jpar][grp ^ 1][my_row];
                 const float best = fminf(vb_, ob);
-                const float xm = misc->grp_x[jpar][grp][my_row], xo = misc->grp_x[jpar][grp ^ 1][my_row];
+                const float xo = misc->grp_x[jpar][grp ^ 1][my_row];
                 const float tol = fabsf(best) * 6.2e-5f;
                 const float xbest = vb_ + tol < ob ? xm : (ob + tol < vb_ ? xo : fmaxf(xm, xo));
                 // Certificate: a code can be the exact argmin only if its optimistic score is <= T.
@@ -1116,9 +1149,11 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     // ring stage: one 64-feature slice of a chunk; paired: MY half of a whole chunk (all slices + norm slices)
     const uint32_t stage_bytes = pair ? (uint32_t)(d / KSLICE) * (tr::B_STAGE_BYTES / 2) + tr::NSLICE_BYTES / 2
                                       : tr::B_STAGE_BYTES + tr::NSLICE_BYTES;
+    // allowance byte tables of two stages (k0_bound): in shared memory while they are small, else read from global
+    const uint32_t tab_bytes = 2u * (uint32_t)Kpad <= 4096u ? 2u * (uint32_t)Kpad : 0u;
     p.off_stg = (uint32_t)p.nslots * a_bytes;
     p.off_B = p.off_stg + stg_bytes;
-    const uint32_t fixed = p.off_B + misc_bytes + 1024;
+    const uint32_t fixed = p.off_B + misc_bytes + tab_bytes + 1024;
     int ns = ((uint32_t)smem_max > fixed) ? (int)(((uint32_t)smem_max - fixed) / stage_bytes) : 0;
     if (ns > tr::MAX_RING) ns = tr::MAX_RING;
     if (ns < 2) {
@@ -1127,7 +1162,8 @@ int rvq_launch_tr(const float* x, long long N, long long L, long long sb, long l
     }
     p.nstage = ns;
     p.off_misc = (p.off_B + (uint32_t)ns * stage_bytes + 1023u) / 1024u * 1024u;
-    const uint32_t smem_total = p.off_misc + misc_bytes + 1024;
+    p.off_tab = tab_bytes ? p.off_misc + misc_bytes : 0u;
+    const uint32_t smem_total = p.off_misc + misc_bytes + tab_bytes + 1024;
 
     EncodeTiledFn encode = get_encode_tiled_tr();
     if (!encode) {

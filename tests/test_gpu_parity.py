@@ -332,6 +332,13 @@ def test_filter_scores_match_fp16_reference():
         a_h = (x * rs[:, None]).half().double()
         b_h = op.reshape(2, Kpad, d)[1].double()
         ref = a_h @ b_h.t() + ((rs / sb)[:, None] * nrm[:2 * Kpad].reshape(2, Kpad)[1][None, :]).double()
+        # codes above the stage's norm cap: the kernel's scores are optimistic by rs_row * xc_k in the 256-code chunks
+        # that hold one (NormLayout, csrc/common.cuh; this entry point runs the generic kernel)
+        xc = nrm[9 * 2 * Kpad:10 * 2 * Kpad].reshape(2, Kpad)[1].double()
+        f0 = 10 * 2 * Kpad + 2 * Kpad // 4          # floats before the flags: norm, slices (8x), xc, byte table
+        flag = nrm[f0:f0 + 2 * (Kpad // 256)].view(torch.int32).reshape(2, Kpad // 256)[1]
+        rs_row = (x.double().pow(2).sum(1).sqrt() * 1.00002 * rs.double())
+        ref = ref - rs_row[:, None] * (xc * flag.repeat_interleave(256).bool())[None, :]
         err = (scores.double() - ref).abs()[:, :K].max()
         assert not torch.isnan(scores[:, :K]).any()
         assert err <= 2e-6 * ref[:, :K].abs().max(), (K, d, float(err))

@@ -27,10 +27,10 @@ def test_argument_checks_need_no_gpu():
     lib = _lib.load()
     ob, nb, mb = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
     assert lib.rvq_prepared_bytes(8, 1000, 128, ctypes.byref(ob), ctypes.byref(nb), ctypes.byref(mb)) == 0
-    # norms: fp32 [nq, Kpad], their fp16 operand slices (32 bytes per code), the two per-code allowance factors fp32
-    # [nq, Kpad] each and one int flag per 256-code chunk (NormLayout, csrc/common.cuh)
+    # norms: fp32 [nq, Kpad], their fp16 operand slices (32 bytes per code), the per-code allowance factor fp32
+    # [nq, Kpad], its byte table [nq, Kpad] and one int flag per 256-code chunk (NormLayout, csrc/common.cuh)
     assert ob.value == 8 * 1024 * 128 * 2 and mb.value == 8 * 8 * 4
-    assert nb.value == 8 * 1024 * (4 + 32 + 4 + 4) + 8 * (1024 // 256) * 4
+    assert nb.value == 8 * 1024 * (4 + 32 + 4 + 1) + 8 * (1024 // 256) * 4
     assert lib.rvq_prepared_bytes(0, 1, 1, None, None, None) == -1
     assert b"positive" in lib.rvq_last_error()
     n = ctypes.c_size_t()
