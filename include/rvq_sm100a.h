@@ -62,9 +62,13 @@ int rvq_device_supported(int device);
 
 /* Sizes (HOST pointers out) of the derived codebook operands written by rvq_prepare_codebooks:
  *   op_bytes   : fp16 [nq, Kpad, d]  = -2 * 2^b_q * C_q            (UMMA B operand, K-major rows)
- *   norm_bytes : fp32 [nq, Kpad]     = 2^(2 b_q) * ||c||^2, padding codes = 2^100; followed by the same norms
- *                as fp16 UMMA operand slices [nq, Kpad/128, 4096 bytes] (three exact 11-bit pieces per code)
- *   meta_bytes : fp32 [nq, 8]        = {2^b_q, max_k ||c_k||_2, max |c|, K_valid, nq prepared, 0...} */
+ *   norm_bytes : fp32 [nq, Kpad]     = 2^(2 b_q) * ||c||^2 (minus the folded allowance term of the codes above the
+ *                stage's norm cap), padding codes = 2^100; followed by the same norms as fp16 UMMA operand slices
+ *                [nq, Kpad/128, 4096 bytes] (three exact 11-bit pieces per code + the allowance column), the first
+ *                allowance factor fp32 [nq, Kpad], the allowance byte table [nq, Kpad] and one int flag per
+ *                256-code chunk (opaque to the caller: written by rvq_prepare_codebooks, read by rvq_encode;
+ *                DESIGN.md section 3 "Per-code bound")
+ *   meta_bytes : fp32 [nq, 8]        = {2^b_q, norm cap / 2^b_q, max |c|, K_valid, nq prepared, U2, max_k ||c_k||_2, U1} */
 int rvq_prepared_bytes(int nq, int K, int d, size_t* op_bytes, size_t* norm_bytes, size_t* meta_bytes);
 
 /* K0. Derive the tensor-core operands from the fp32 master codebooks cb[nq, K, d].
