@@ -128,8 +128,8 @@ __global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad
 // (generic kernel: xc array, xflag per 256-code chunk).
 // The cap is the stage's lower-quartile norm (cs_max itself when the norms are concentrated, max <= 1.25 x quartile:
 // freshly initialised codebooks - no code is flagged and the generic kernel's epilogue stays on its short path).
-// Measured on C3 (profiles/r2g_probe_*.log): cap 1.5 x p25 14.66 / 15.41 ms (1 / 8 shards), p25 13.86 / 14.72,
-// the stage minimum 14.44 / 14.84.
+// Measured on C3 (profiles/r2g_probe_*.log, encode kernel with statistics after 150 updates, 1 / 8 shards' state):
+// cap 1.5 x p25 14.66 / 15.41 ms, cap p25 13.86 / 14.72 ms (16.13 / 19.07 ms with the stage maximum).
 #ifndef RVQ_CAP_DIV
 #define RVQ_CAP_DIV 4
 #endif
