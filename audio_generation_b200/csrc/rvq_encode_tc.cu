@@ -53,6 +53,7 @@ struct EncParams {
     float* r_scratch;  // per-CTA [128, d] fp32 when the residual tile does not fit in shared memory
     int num_tiles, nstage, nslots, r_pitch;
     int cluster;  // CTAs per cluster sharing the codebook stream (TMA multicast)
+    int tile_rows;  // frames per tile (<= TILE_M): small calls spread over more SMs with partly filled tiles
     uint32_t off_B, off_misc;  // A tiles (one per slot) at offset 0
     float* dbg_scores;                // [128, Kpad] (bring-up hook) or null
     float* dbg_rowscale;              // [128] or null
@@ -606,6 +607,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         unsigned long long n_dirty_tot = 0, n_two_tot = 0, n_jobs = 0, n_score_pass = 0;
         double commit_local = 0.0;
 
+        // rows the update passes walk (whole passes of 32 frames; the rest of the 128 lanes stays zero)
+        const int tile_rows = p.tile_rows;
+        const int rows_eff = d == 128 ? (tile_rows + 63) & ~63 : (tile_rows + ROWS_PER_PASS - 1) & ~(ROWS_PER_PASS - 1);
         auto rtile = [&](int sl) {
             RTile rt;
             rt.base = p.r_scratch + ((size_t)blockIdx.x * 2 + sl) * TILE_M * p.r_pitch;
@@ -616,21 +620,32 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
         auto load_tile = [&](int sl, int tile) {
             const RTile rt = rtile(sl);
             uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
-            const long long n0 = (long long)tile * TILE_M;
+            const long long n0 = (long long)tile * tile_rows;
             if (!row_major) {
-                // frames-fastest copy (coalesced along the frame axis of the reference's (B, d, L) storage)
-                for (int row = u; row < TILE_M; row += UPD_THREADS) {
+                // The reference's (B, d, L) storage: frames are the fastest axis.  A warp takes 32 frames x 8 features:
+                // lane = frame (coalesced 128-byte reads per feature), the eight loads of a lane are independent (one
+                // memory round trip per unit), and they leave as two 16-byte stores into the lane's residual row.
+                const int nrb = rows_eff / 32, units = nrb * (d / 8);
+#pragma unroll 1
+                for (int unit = uwarp; unit < units; unit += UPD_WARPS) {
+                    const int row = (unit % nrb) * 32 + (u & 31), c0 = (unit / nrb) * 8;
                     const long long n = n0 + row;
-                    const float* xr = p.x + (n < p.N ? p.ad.row(n) : 0);
-                    for (int c = 0; c < d; ++c) *rt.at(row, c) = (n < p.N) ? xr[(long long)c * p.ad.sd] : 0.f;
+                    const bool ok = row < tile_rows && n < p.N;
+                    const float* xr = p.x + (ok ? p.ad.row(n) : 0) + (long long)c0 * p.ad.sd;
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = ok ? __ldcs(xr + (long long)j * p.ad.sd) : 0.f;
+                    *reinterpret_cast<float4*>(rt.at(row, c0)) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(rt.at(row, c0 + 4)) = make_float4(v[4], v[5], v[6], v[7]);
                 }
                 named_bar_sync(BAR_UPD, UPD_THREADS);
             }
 #pragma unroll 1
             for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
                 const long long n = n0 + row;
-                const float* xr = row_major ? p.x + (n < p.N ? p.ad.row(n) : 0) : rt.at(row, 0);
-                init_row(p, misc, a_tile, rt, sl, row, xr, row_major ? n < p.N : true, sub, row_major);
+                const bool ok = row < tile_rows && n < p.N;
+                const float* xr = row_major ? p.x + (ok ? p.ad.row(n) : 0) : rt.at(row, 0);
+                init_row(p, misc, a_tile, rt, sl, row, xr, row_major ? ok : row < rows_eff, sub, row_major);
             }
             fence_proxy_async_smem();
             mbar_arrive(&misc->a_ready[sl]);
@@ -643,7 +658,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             const int sl = job.slot % nslots;
             const int q = job.q, q_abs = p.q_begin + q;
             const int tile = blockIdx.x + job.i * gridDim.x;
-            const long long n0 = (long long)tile * TILE_M;
+            const long long n0 = (long long)tile * tile_rows;
+            auto frame_ok = [&](int row) { return row < tile_rows && n0 + row < p.N; };
             const RTile rt = rtile(sl);
             uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
             long long t0 = clock64();
@@ -657,7 +673,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             // ---------------- classify the frames: certified (one candidate), re-rank list, exact-scan list
             const long long ts0 = clock64();
             const int Kv_q = (int)p.cb_meta[(size_t)q_abs * META_STRIDE + 3];
-            if (u < TILE_M) {
+            if (u < rows_eff) {
                 const uint32_t r0 = misc->g_rows[sl][0][u], r1 = misc->g_rows[sl][1][u];
                 const uint32_t c0 = misc->g_cols[sl][0][u], c1 = misc->g_cols[sl][1][u];
                 const int n0 = (int)((r0 >> 27) & 3u) * __popc(c0), n1 = (int)((r1 >> 27) & 3u) * __popc(c1);
@@ -714,7 +730,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             // ---------------- gather, residual update, statistics, next operand
             auto post_row = [&](int row, bool active, int kwin, float sq) {
                 const long long n = n0 + row;
-                if (active && sub == 0 && n < p.N) {
+                if (active && sub == 0 && frame_ok(row)) {
                     __stcs(p.idx + n * nq + q, (long long)kwin);
                     commit_local += (double)sq;
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
@@ -722,23 +738,23 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             };
             if (d == 128) {
 #pragma unroll 1
-                for (int r0 = slot16; r0 < TILE_M; r0 += 2 * ROWS_PER_PASS) {
+                for (int r0 = slot16; r0 < rows_eff; r0 += 2 * ROWS_PER_PASS) {
                     const int r1 = r0 + ROWS_PER_PASS;
                     const bool a0 = misc->win[sl][r0] >= 0, a1 = misc->win[sl][r1] >= 0;
                     const int k0 = a0 ? misc->win[sl][r0] : 0, k1 = a1 ? misc->win[sl][r1] : 0;
                     float sq0, sq1;
-                    apply_two_rows_128(p, misc, a_tile, rt, sl, r0, r1, a0, a1, n0 + r0 < p.N, n0 + r1 < p.N, k0, k1,
+                    apply_two_rows_128(p, misc, a_tile, rt, sl, r0, r1, a0, a1, frame_ok(r0), frame_ok(r1), k0, k1,
                                        q_abs, next_q_abs, sub, sq0, sq1);
                     post_row(r0, a0, k0, sq0);
                     post_row(r1, a1, k1, sq1);
                 }
             } else {
 #pragma unroll 1
-                for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
+                for (int row = slot16; row < rows_eff; row += ROWS_PER_PASS) {
                     const bool active = misc->win[sl][row] >= 0;
                     const int kwin = active ? misc->win[sl][row] : 0;
                     float sq;
-                    apply_row(p, misc, a_tile, rt, sl, row, active, n0 + row < p.N, kwin, q_abs, next_q_abs, sub, &sq, sc);
+                    apply_row(p, misc, a_tile, rt, sl, row, active, frame_ok(row), kwin, q_abs, next_q_abs, sub, &sq, sc);
                     post_row(row, active, kwin, sq);
                 }
             }
@@ -777,8 +793,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         if (bk < 0 || bk >= Kv) bk = 0;
                         const long long n = n0 + row;
                         float sq;
-                        apply_row(p, misc, a_tile, rt, sl, row, lane < 8, n < p.N, bk, q_abs, next_q_abs, sub, &sq, sc);
-                        if (lane == 0 && n < p.N) {
+                        apply_row(p, misc, a_tile, rt, sl, row, lane < 8, frame_ok(row), bk, q_abs, next_q_abs, sub, &sq, sc);
+                        if (lane == 0 && frame_ok(row)) {
                             __stcs(p.idx + n * nq + q, (long long)bk);
                             atomicAdd(&misc->commit_acc[q], (double)sq);
                             if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + bk, 1.f);
@@ -798,9 +814,9 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 named_bar_sync(BAR_UPD, UPD_THREADS);  // dirty rows were finished by other warps
                 if (row_major) {
 #pragma unroll 1
-                    for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
+                    for (int row = slot16; row < rows_eff; row += ROWS_PER_PASS) {
                         const long long n = n0 + row;
-                        if (n < p.N) {
+                        if (frame_ok(row)) {
                             const long long off = p.ad.row(n);
                             for (int c = sub * 4; c < d; c += 32) {
                                 const float4 xv = __ldcs(reinterpret_cast<const float4*>(p.x + off + c));
@@ -815,14 +831,21 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         }
                     }
                 } else {
-                    for (int row = u; row < TILE_M; row += UPD_THREADS) {
-                        const long long n = n0 + row;
-                        if (n < p.N) {
-                            const long long off = p.ad.row(n);
-                            for (int c = 0; c < d; ++c) {
-                                const long long o = off + (long long)c * p.ad.sd;
-                                p.xq[o] = p.x[o] - *rt.at(row, c);
-                            }
+                    // frames-fastest storage: the same 32 frames x 8 features units as the tile load
+                    const int nrb = rows_eff / 32, units = nrb * (d / 8);
+#pragma unroll 1
+                    for (int unit = uwarp; unit < units; unit += UPD_WARPS) {
+                        const int row = (unit % nrb) * 32 + (u & 31), c0 = (unit / nrb) * 8;
+                        if (frame_ok(row)) {
+                            const long long off = p.ad.row(n0 + row) + (long long)c0 * p.ad.sd;
+                            const float4 ra = *reinterpret_cast<const float4*>(rt.at(row, c0));
+                            const float4 rb = *reinterpret_cast<const float4*>(rt.at(row, c0 + 4));
+                            const float r8[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = __ldcs(p.x + off + (long long)j * p.ad.sd);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) __stcs(p.xq + off + (long long)j * p.ad.sd, v[j] - r8[j]);
                         }
                     }
                 }
@@ -957,12 +980,23 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
         set_error("rvq_encode: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
         return RVQ_ERR_CUDA;
     }
-    const int num_tiles = (int)((N + TILE_M - 1) / TILE_M);
+    // Small calls (the reference's training and inference shapes: 136 ... 4000 frames) would fill a handful of SMs with
+    // whole 128-frame tiles and leave the rest idle, while a tile-stage costs the update warps one pass per 32 frames.
+    // Spread them instead: tiles of ceil(N / SMs) frames rounded up to a whole pass.  The MMA still runs M = 128 (the
+    // unused lanes hold zeros); the codebook stream per SM is the same as for a full tile.
+    int tile_rows = TILE_M;
+    if (!dbg_scores && N < (long long)num_sms * TILE_M) {
+        const long long per_sm = (N + num_sms - 1) / num_sms;
+        tile_rows = (int)((per_sm + 31) / 32 * 32);
+        if (tile_rows > TILE_M) tile_rows = TILE_M;
+    }
+    const int num_tiles = (int)((N + tile_rows - 1) / tile_rows);
     // persistent grid of whole clusters: as many as the tiles need, at most one CTA per SM
     const int want_clusters = (num_tiles + CL - 1) / CL, max_clusters = num_sms / CL;
     const int grid = (want_clusters < max_clusters ? want_clusters : max_clusters) * CL;
     EncParams p{};
     p.cluster = CL;
+    p.tile_rows = tile_rows;
     p.x = x;
     p.N = N;
     p.ad = RowAddrT{L, sb, sl, sd};
