@@ -821,11 +821,13 @@ rvq_encode_fr_kernel(const __grid_constant__ CUtensorMap tmap_b, const Params p)
                         tmem_ld_32x32(t_r + c0, v);
                         tmem_ld_wait();
                         if (valid) {
+                            // loads before stores: x and xq may alias as far as the compiler knows
+                            float xv[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const long long o = off + (long long)(c0 + j) * p.ad.sd;
-                                p.xq[o] = p.x[o] - __uint_as_float(v[j]);
-                            }
+                            for (int j = 0; j < 32; ++j) xv[j] = __ldcs(p.x + off + (long long)(c0 + j) * p.ad.sd);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                __stcs(p.xq + off + (long long)(c0 + j) * p.ad.sd, xv[j] - __uint_as_float(v[j]));
                         }
                     }
                 }

@@ -614,7 +614,7 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
                         // frames-fastest storage (the reference's (B, d, L) tensor): lanes = consecutive frames
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            v[j] = valid ? __float_as_uint(p.x[off + (long long)(c0 + j) * p.ad.sd]) : 0u;
+                            v[j] = valid ? __float_as_uint(__ldcs(p.x + off + (long long)(c0 + j) * p.ad.sd)) : 0u;
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -1011,11 +1011,14 @@ rvq_encode_tr_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_co
                                 *reinterpret_cast<float4*>(stg_row + c0 + j) = xv;
                             }
                         } else if (valid) {
+                            // all 32 loads before the first store: x and xq may alias as far as the compiler knows,
+                            // and a load behind every store made this 32 dependent memory round trips per piece
+                            float xv[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const long long o = off + (long long)(c0 + j) * p.ad.sd;
-                                p.xq[o] = p.x[o] - __uint_as_float(v[j]);
-                            }
+                            for (int j = 0; j < 32; ++j) xv[j] = __ldcs(p.x + off + (long long)(c0 + j) * p.ad.sd);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                __stcs(p.xq + off + (long long)(c0 + j) * p.ad.sd, xv[j] - __uint_as_float(v[j]));
                         }
                     }
                     if (row_major) {

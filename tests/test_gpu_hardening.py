@@ -411,3 +411,42 @@ def test_encode_call_is_cuda_graph_capturable(d, L):
             xq_e, idx_e, commit_e = m(xv)
             assert torch.equal(idx_g, idx_e) and torch.equal(xq_g, xq_e)
             assert abs(float(commit_g) - float(commit_e)) <= 1e-6 * abs(float(commit_e))
+
+
+# ------------------------------------------------------------------- partly filled tiles (small calls) and (B, d, L) storage
+@pytest.mark.parametrize("d", [256, 512])
+@pytest.mark.parametrize("layout", ["rows", "bdl"])
+def test_small_calls_with_partly_filled_tiles_are_bit_identical(d, layout):
+    """Calls below 148 x 128 frames run tiles of ceil(N / SMs) frames rounded to 32 (rvq_encode_tc.cu: tile_rows): every
+    tile size from one pass to the full tile, frame counts on both sides of each boundary, in the row layout and in the
+    reference's (B, d, L) storage, against the exact-scan kernel (bitwise: it never uses tiles of this kind) - encode
+    and the EMA statistics of an update step."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    nq, K = 4, 300
+    torch.manual_seed(3)
+    m = quantizer(nq, K, d, vq_cutoff_freq=0.0, use_som=False).cuda()
+    ref = quantizer(nq, K, d, vq_cutoff_freq=0.0, use_som=False, algo="exact_scan").cuda()
+    ref.load_state_dict(m.state_dict())
+    for N in [1, 31, 33, sms * 32 - 1, sms * 32 + 1, sms * 64 + 5, sms * 96 + 1, sms * 128 - 1, sms * 128 + 7]:
+        if layout == "rows":
+            x = torch.randn(N, d, device="cuda")
+        else:
+            B = 3 if N % 3 == 0 and N >= 3 else 1
+            x = torch.randn(B, d, N // B, device="cuda").permute(0, 2, 1)      # vae.py:313: a VIEW, features strided
+            assert not x.is_contiguous() or N == 1
+        m.eval(), ref.eval()
+        with torch.no_grad():
+            xq, idx, commit = m(x)
+            xq_e, idx_e, commit_e = ref(x)
+        assert torch.equal(idx, idx_e), (N, layout)
+        assert torch.equal(xq, xq_e), (N, layout)
+        assert xq.stride() == x.stride() or N == 1
+    # one update step on a partly filled tiling: same statistics, same refreshed codebooks
+    m.train(), ref.train()
+    x = torch.randn(2, d, 150, device="cuda").permute(0, 2, 1) if layout == "bdl" else torch.randn(300, d, device="cuda")
+    with torch.no_grad():
+        _, idx, _ = m(x, None, update_codebook=True)
+        _, idx_e, _ = ref(x, None, update_codebook=True)
+    assert torch.equal(idx, idx_e)
+    assert torch.equal(m.ema_count, ref.ema_count)
+    assert torch.allclose(m.codebooks, ref.codebooks, rtol=1e-5, atol=1e-6)       # float atomics: summation order only
