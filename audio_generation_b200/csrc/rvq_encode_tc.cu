@@ -306,18 +306,30 @@ __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t
                                          bool stream_x) {
     const int d = p.d;
     float sq = 0.f, amax = 0.f;
-#pragma unroll 2
-    for (int c = sub * 4; c < d; c += 32) {
-        // x streams through L2 once (evict-first) so that it does not push the residual scratch out
-        const float4 v = row_valid ? (stream_x ? __ldcs(reinterpret_cast<const float4*>(xr + c))
-                                               : *reinterpret_cast<const float4*>(xr + c))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(rt.at(row, c)) = v;
-        sq = fmaf(v.x, v.x, sq);
-        sq = fmaf(v.y, v.y, sq);
-        sq = fmaf(v.z, v.z, sq);
-        sq = fmaf(v.w, v.w, sq);
-        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    const int np = d / 32;  // 16-byte pieces per lane
+#pragma unroll 1
+    for (int i0 = 0; i0 < np; i0 += 8) {
+        // eight pieces per lane in flight (one memory round trip per 256 features; d = 512 took sixteen dependent ones)
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = sub * 4 + (i0 + i) * 32;
+            // x streams through L2 once (evict-first) so that it does not push the residual scratch out
+            v[i] = (row_valid && i0 + i < np) ? (stream_x ? __ldcs(reinterpret_cast<const float4*>(xr + c))
+                                                           : *reinterpret_cast<const float4*>(xr + c))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i0 + i < np) {
+                *reinterpret_cast<float4*>(rt.at(row, sub * 4 + (i0 + i) * 32)) = v[i];
+                sq = fmaf(v[i].x, v[i].x, sq);
+                sq = fmaf(v[i].y, v[i].y, sq);
+                sq = fmaf(v[i].z, v[i].z, sq);
+                sq = fmaf(v[i].w, v[i].w, sq);
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+            }
+        }
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
@@ -330,10 +342,15 @@ __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t
     bool force_exact = !isfinite(sq);
     const int a = pick_row_exp(amax, b, force_exact);
     const float sa = exp2i(a);
-#pragma unroll 2
-    for (int c = sub * 4; c < d; c += 32) {
-        const float4 v = *reinterpret_cast<const float4*>(rt.at(row, c));  // written by this lane above
-        store_a4(smem_a, row, c, v, sa);
+#pragma unroll 1
+    for (int i0 = 0; i0 < np; i0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)  // (written by this lane above; every element assigned: no local-memory demotion)
+            v[i] = *reinterpret_cast<const float4*>(rt.at(row, sub * 4 + min(i0 + i, np - 1) * 32));
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i0 + i < np) store_a4(smem_a, row, sub * 4 + (i0 + i) * 32, v[i], sa);
     }
     if (sub == 0) {
         misc->row_amax[sl][row] = amax;
@@ -818,15 +835,28 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         const long long n = n0 + row;
                         if (frame_ok(row)) {
                             const long long off = p.ad.row(n);
-                            for (int c = sub * 4; c < d; c += 32) {
-                                const float4 xv = __ldcs(reinterpret_cast<const float4*>(p.x + off + c));
-                                const float4 rv = *reinterpret_cast<const float4*>(rt.at(row, c));
-                                float4 o;
-                                o.x = xv.x - rv.x;
-                                o.y = xv.y - rv.y;
-                                o.z = xv.z - rv.z;
-                                o.w = xv.w - rv.w;
-                                __stcs(reinterpret_cast<float4*>(p.xq + off + c), o);
+                            // four pieces of x and of the residual per lane in flight, then the stores (a load
+                            // behind every store would be a dependent round trip: xq may alias as far as nvcc knows)
+#pragma unroll 1
+                            for (int c0 = sub * 4; c0 < d; c0 += 128) {
+                                float4 xv[4], rv[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int c = min(c0 + i * 32, d - 32 + sub * 4);  // (every element assigned)
+                                    xv[i] = __ldcs(reinterpret_cast<const float4*>(p.x + off + c));
+                                    rv[i] = *reinterpret_cast<const float4*>(rt.at(row, c));
+                                }
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    if (c0 + i * 32 < d) {
+                                        float4 o;
+                                        o.x = xv[i].x - rv[i].x;
+                                        o.y = xv[i].y - rv[i].y;
+                                        o.z = xv[i].z - rv[i].z;
+                                        o.w = xv[i].w - rv[i].w;
+                                        __stcs(reinterpret_cast<float4*>(p.xq + off + c0 + i * 32), o);
+                                    }
+                                }
                             }
                         }
                     }
