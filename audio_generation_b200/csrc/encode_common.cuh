@@ -20,9 +20,11 @@ struct RowAddrT {
 
 
 // byte offset of fp16 element (row, col) inside the A tile (d/64 slices of [128 rows x 128 B], SWIZZLE_128B)
-__device__ __forceinline__ uint32_t a_tile_offset(int row, int col) {
+// (slice_bytes < A_SLICE_BYTES: tiles that hold fewer than 128 frames keep only those rows of every slice; the MMA
+// still reads 128 rows from a slice's base - the lanes beyond the tile see the following slices' bytes and are ignored)
+__device__ __forceinline__ uint32_t a_tile_offset(int row, int col, uint32_t slice_bytes = A_SLICE_BYTES) {
     const int slice = col >> 6, c = col & 63;
-    return (uint32_t)slice * A_SLICE_BYTES + (uint32_t)row * 128u + ((((uint32_t)c >> 3) ^ ((uint32_t)row & 7u)) << 4) +
+    return (uint32_t)slice * slice_bytes + (uint32_t)row * 128u + ((((uint32_t)c >> 3) ^ ((uint32_t)row & 7u)) << 4) +
            (((uint32_t)c & 7u) << 1);
 }
 

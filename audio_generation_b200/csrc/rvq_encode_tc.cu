@@ -36,6 +36,7 @@ constexpr int MAX_NQ = 64;
 constexpr uint32_t B_STAGE_BYTES = CHUNK_N * KSLICE * 2;  // 32 KiB
 constexpr uint32_t BAR_SCAN = 1;  // named barrier of the 256 scan threads
 constexpr uint32_t BAR_UPD = 2;   // named barrier of the update threads
+constexpr int ITEM_CAP = 256;     // re-rank work items per tile-stage (frames beyond take the exact scan)
 
 struct EncParams {
     const float* x;
@@ -54,6 +55,7 @@ struct EncParams {
     int num_tiles, nstage, nslots, r_pitch;
     int cluster;  // CTAs per cluster sharing the codebook stream (TMA multicast)
     int tile_rows;  // frames per tile (<= TILE_M): small calls spread over more SMs with partly filled tiles
+    int a_rows;     // rows of every operand slice kept in shared memory (32 | 64 | 128, >= tile_rows)
     uint32_t off_B, off_misc;  // A tiles (one per slot) at offset 0
     float* dbg_scores;                // [128, Kpad] (bring-up hook) or null
     float* dbg_rowscale;              // [128] or null
@@ -75,8 +77,15 @@ struct __align__(16) Misc {
     uint16_t dirty_cols[2][TILE_M];          // per exact-scan frame: columns to scan
     int win[2][TILE_M];                      // [slot][frame]: selected code, -1 = exact scan pending
     int dirty_rows[2][TILE_M];
-    int score_rows[2][TILE_M];
-    int score_count[2];
+    // exact re-rank work items: one PAIR of candidates of one frame each, so that a frame with four candidates is
+    // scored by two 8-lane groups at once instead of in two dependent rounds (one buffer: jobs re-rank one at a time)
+    int score_count[2];                 // [0] items, [1] frames with several candidates (counter only)
+    int n_items;                        // items of the current job (published between two barriers)
+    uint16_t item[ITEM_CAP];            // frame | pair << 8
+    float item_s[ITEM_CAP];             // best exact score of the pair
+    int item_k[ITEM_CAP];               // its code
+    uint16_t row_item0[TILE_M];         // first item of the frame
+    uint8_t row_nitem[TILE_M];          // number of items of the frame (0: not a re-rank frame)
     float dirty_s[8];
     int dirty_k[8];
     double commit_acc[MAX_NQ];
@@ -101,20 +110,20 @@ __device__ __forceinline__ void write_row_consts(const EncParams& p, Misc* misc,
     if (p.dbg_rowscale) p.dbg_rowscale[row] = exp2i(a);
 }
 
-__device__ __forceinline__ void store_a4(uint8_t* smem_a, int row, int c, float4 v, float sa) {
+__device__ __forceinline__ void store_a4(uint8_t* smem_a, int row, int c, float4 v, float sa, uint32_t asb) {
     const __half2 h01 = __floats2half2_rn(v.x * sa, v.y * sa);
     const __half2 h23 = __floats2half2_rn(v.z * sa, v.w * sa);
     uint2 pk;
     pk.x = *reinterpret_cast<const uint32_t*>(&h01);
     pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-    *reinterpret_cast<uint2*>(smem_a + a_tile_offset(row, c)) = pk;
+    *reinterpret_cast<uint2*>(smem_a + a_tile_offset(row, c, asb)) = pk;
 }
 
 // NP float4 pieces per lane of one frame: r <- r - c (+ statistics, norms, next operand)
 template <int NP>
 __device__ __forceinline__ void apply_seg(uint8_t* smem_a, const RTile& rt, int row, const float* __restrict__ cw,
                                           float* __restrict__ ssum, int c0, bool write_a, float sa, float& sq,
-                                          float& amax) {
+                                          float& amax, uint32_t asb) {
     float4 rv[NP], cv[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -136,7 +145,7 @@ __device__ __forceinline__ void apply_seg(uint8_t* smem_a, const RTile& rt, int 
         sq = fmaf(nr.z, nr.z, sq);
         sq = fmaf(nr.w, nr.w, sq);
         amax = fmaxf(amax, fmaxf(fmaxf(fabsf(nr.x), fabsf(nr.y)), fmaxf(fabsf(nr.z), fabsf(nr.w))));
-        if (write_a) store_a4(smem_a, row, c, nr, sa);
+        if (write_a) store_a4(smem_a, row, c, nr, sa, asb);
     }
 }
 
@@ -179,18 +188,19 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
         a = pick_row_exp(bound, b, force_exact);
         sa = exp2i(a);
     }
+    const uint32_t asb = (uint32_t)p.a_rows * 128u;
     if (active) {
         const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d;
         float* ssum = (p.stats_sum && row_valid) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d : nullptr;
         int c0 = sub * 4;
 #pragma unroll 1
         // 256 features per step when possible: one L2 round trip covers eight pieces of the frame and of the code
-        for (; c0 + 256 <= d + sub * 4; c0 += 256) apply_seg<8>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
+        for (; c0 + 256 <= d + sub * 4; c0 += 256) apply_seg<8>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax, asb);
         if (d & 128) {
-            apply_seg<4>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
+            apply_seg<4>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax, asb);
             c0 += 128;
         }
-        if (d & 64) apply_seg<2>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax);
+        if (d & 64) apply_seg<2>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax, asb);
     }
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
@@ -350,7 +360,7 @@ __device__ __forceinline__ void init_row(const EncParams& p, Misc* misc, uint8_t
             v[i] = *reinterpret_cast<const float4*>(rt.at(row, sub * 4 + min(i0 + i, np - 1) * 32));
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (i0 + i < np) store_a4(smem_a, row, sub * 4 + (i0 + i) * 32, v[i], sa);
+            if (i0 + i < np) store_a4(smem_a, row, sub * 4 + (i0 + i) * 32, v[i], sa, (uint32_t)p.a_rows * 128u);
     }
     if (sub == 0) {
         misc->row_amax[sl][row] = amax;
@@ -370,7 +380,8 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
     const int n_ks = d / KSLICE;
     const int n_chunks = p.Kpad / CHUNK_N;
     const int nstage = p.nstage;
-    const uint32_t a_tile_bytes = (uint32_t)n_ks * A_SLICE_BYTES;
+    const uint32_t a_slice_bytes = (uint32_t)p.a_rows * 128u;
+    const uint32_t a_tile_bytes = (uint32_t)n_ks * a_slice_bytes;
     // every CTA of a cluster walks the same job sequence (tiles past the end are empty: all frames invalid)
     const int n_local = (p.num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int CL = p.cluster;
@@ -477,7 +488,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                             umma_commit_mc(&misc->empty[st], cmask);
                         else
                             umma_commit(&misc->empty[st]);
-                        adesc += (uint64_t)(A_SLICE_BYTES >> 4);
+                        adesc += (uint64_t)(a_slice_bytes >> 4);
                         if (++st == (uint32_t)nstage) {
                             st = 0;
                             ph ^= 1u;
@@ -658,7 +669,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 named_bar_sync(BAR_UPD, UPD_THREADS);
             }
 #pragma unroll 1
-            for (int row = slot16; row < TILE_M; row += ROWS_PER_PASS) {
+            for (int row = slot16; row < p.a_rows; row += ROWS_PER_PASS) {  // (the operand tile holds a_rows rows)
                 const long long n = n0 + row;
                 const bool ok = row < tile_rows && n < p.N;
                 const float* xr = row_major ? p.x + (ok ? p.ad.row(n) : 0) : rt.at(row, 0);
@@ -694,55 +705,81 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 const uint32_t r0 = misc->g_rows[sl][0][u], r1 = misc->g_rows[sl][1][u];
                 const uint32_t c0 = misc->g_cols[sl][0][u], c1 = misc->g_cols[sl][1][u];
                 const int n0 = (int)((r0 >> 27) & 3u) * __popc(c0), n1 = (int)((r1 >> 27) & 3u) * __popc(c1);
-                int w = -1;
-                if (((r0 | r1) & G_OVER) || n0 + n1 == 0) {
+                int w = -1, nitem = 0;
+                bool dirty = ((r0 | r1) & G_OVER) || n0 + n1 == 0;
+                if (!dirty && n0 + n1 == 1) {
+                    w = n0 ? (int)((r0 & IT_MASK) * 16u) + __ffs(c0) - 1 : (int)((r1 & IT_MASK) * 16u) + __ffs(c1) - 1;
+                    if (w >= Kv_q) w = 0;  // cannot happen (padding codes score 2^100); keeps the gather in bounds
+                } else if (!dirty) {
+                    const int npairs = (n0 + n1 + 1) >> 1;
+                    const int pos = npairs <= 16 ? atomicAdd(&misc->score_count[0], npairs) : ITEM_CAP;
+                    if (pos + npairs <= ITEM_CAP) {
+                        for (int t = 0; t < npairs; ++t) misc->item[pos + t] = (uint16_t)(u | (t << 8));
+                        misc->row_item0[u] = (uint16_t)pos;
+                        nitem = npairs;
+                        w = 0;  // replaced by the re-rank below
+                        atomicAdd(&misc->score_count[1], 1);
+                    } else {
+                        dirty = true;  // more than 32 candidates (or the item list is full): exact scan of its columns
+                    }
+                }
+                if (dirty) {
                     const int pos = atomicAdd(&misc->dirty_count[sl], 1);
                     misc->dirty_rows[sl][pos] = u;
                     misc->dirty_cols[sl][pos] = (uint16_t)((c0 | c1) ? (c0 | c1) : 0xFFFFu);
-                } else if (n0 + n1 == 1) {
-                    w = n0 ? (int)((r0 & IT_MASK) * 16u) + __ffs(c0) - 1 : (int)((r1 & IT_MASK) * 16u) + __ffs(c1) - 1;
-                    if (w >= Kv_q) w = 0;  // cannot happen (padding codes score 2^100); keeps the gather in bounds
-                } else {
-                    misc->score_rows[sl][atomicAdd(&misc->score_count[sl], 1)] = u;
-                    w = 0;  // replaced by the re-rank below
                 }
+                misc->row_nitem[u] = (uint8_t)nitem;
                 misc->win[sl][u] = w;
             }
             named_bar_sync(BAR_UPD, UPD_THREADS);
-            // ---------------- exact re-rank of the frames with several candidates (compacted list)
-            const int n_score = misc->score_count[sl];
+            // the counters are taken and cleared between two barriers: the next job's classification (which no barrier
+            // separates from the end of this job) finds them zero, and nobody reads them while they change
+            if (u == 0) {
+                misc->n_items = min(misc->score_count[0], ITEM_CAP);
+                n_two_tot += misc->score_count[1];
+                misc->score_count[0] = misc->score_count[1] = 0;
+            }
+            named_bar_sync(BAR_UPD, UPD_THREADS);
+            // ---------------- exact re-rank: one pair of candidates per 8-lane group and round
+            const int n_score = misc->n_items;
             for (int base = 0; base < n_score; base += ROWS_PER_PASS) {
                 const int i = base + slot16;
                 const bool sc = i < n_score;
-                const int row = misc->score_rows[sl][sc ? i : 0];
+                const uint32_t it = misc->item[sc ? i : 0];
+                const int row = (int)(it & 0x7fu), pair = (int)(it >> 8) & 15;  // (masked: entries past a full list are stale)
                 const CandSet cs(misc->g_rows[sl][0][row], misc->g_cols[sl][0][row], misc->g_rows[sl][1][row],
                                  misc->g_cols[sl][1][row]);
-                const int nc = sc ? cs.total() : 0;
-                int nc_max = nc;  // the whole warp walks the longest list of its four frames
-                nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, 8));
-                nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, 16));
-                float bs = __int_as_float(0x7f800000);
-                int kwin = 0x7fffffff;
-#pragma unroll 1
-                for (int j = 0; j < nc_max; j += 2) {
-                    const int c1 = cs.code(j, Kv_q - 1), c2 = cs.code(j + 1, Kv_q - 1);
-                    const float* cc[2] = {cbq + (size_t)c1 * d, cbq + (size_t)c2 * d};
-                    float sv[2];
-                    exact_score8_n<2>(rt.at(row, 0), cc, d, sub, sv);
-                    if (better(sv[0], c1, bs, kwin)) {
-                        bs = sv[0];
-                        kwin = c1;
-                    }
-                    if (better(sv[1], c2, bs, kwin)) {
-                        bs = sv[1];
-                        kwin = c2;
-                    }
+                const int c1 = cs.code(2 * pair, Kv_q - 1), c2 = cs.code(2 * pair + 1, Kv_q - 1);
+                const float* cc[2] = {cbq + (size_t)c1 * d, cbq + (size_t)c2 * d};
+                float sv[2];
+                exact_score8_n<2>(rt.at(row, 0), cc, d, sub, sv);
+                float bs = sv[0];
+                int kwin = c1;
+                if (better(sv[1], c2, bs, kwin)) {
+                    bs = sv[1];
+                    kwin = c2;
                 }
-                if (sc && sub == 0) misc->win[sl][row] = kwin;
+                if (sc && sub == 0) {
+                    misc->item_s[i] = bs;
+                    misc->item_k[i] = kwin;
+                }
                 ++n_score_pass;
             }
-            if (n_score > 0) named_bar_sync(BAR_UPD, UPD_THREADS);  // winners visible to the applying groups
-            n_two_tot += n_score;
+            if (n_score > 0) {
+                named_bar_sync(BAR_UPD, UPD_THREADS);
+                if (u < rows_eff && misc->row_nitem[u] > 0) {
+                    const int i0 = misc->row_item0[u], ni = misc->row_nitem[u];
+                    float bs = misc->item_s[i0];
+                    int kwin = misc->item_k[i0];
+                    for (int t = 1; t < ni; ++t)
+                        if (better(misc->item_s[i0 + t], misc->item_k[i0 + t], bs, kwin)) {
+                            bs = misc->item_s[i0 + t];
+                            kwin = misc->item_k[i0 + t];
+                        }
+                    misc->win[sl][u] = kwin;
+                }
+                named_bar_sync(BAR_UPD, UPD_THREADS);  // winners visible to the applying groups
+            }
             const long long ts1 = clock64();
             // ---------------- gather, residual update, statistics, next operand
             auto post_row = [&](int row, bool active, int kwin, float sq) {
@@ -821,7 +858,6 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                 }
                 if (u == 0) misc->dirty_count[sl] = 0;
             }
-            if (u == 0) misc->score_count[sl] = 0;
             long long t3 = clock64();
             if (next_q_abs >= 0) {
                 fence_proxy_async_smem();
@@ -943,9 +979,9 @@ struct SmemPlan {
     int nstage, nslots;
 };
 
-SmemPlan plan_smem(int d, int smem_max) {
+SmemPlan plan_smem(int d, int smem_max, int a_rows) {
     SmemPlan s{};
-    const uint32_t a_bytes = (uint32_t)(d / KSLICE) * A_SLICE_BYTES;
+    const uint32_t a_bytes = (uint32_t)(d / KSLICE) * (uint32_t)a_rows * 128u;
     const uint32_t misc_bytes = (uint32_t)((sizeof(Misc) + 1023) / 1024 * 1024);
     // two tiles in flight (ping-pong between scan and update warps) if >= 2 ring stages still fit: the epilogue,
     // not the MMA, is the long pole, so a shallow codebook ring costs less than serialising scan and update
@@ -985,7 +1021,25 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     RVQ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     RVQ_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int Kpad = round_up(K, CHUNK_N);
-    const SmemPlan sp = plan_smem(d, smem_max);
+    // Tile size.  Small calls (the reference's training and inference shapes: 136 ... 4000 frames) would fill a handful
+    // of SMs with whole 128-frame tiles and leave the rest idle, while a tile-stage costs the update warps one pass per
+    // 32 frames: they get tiles of ceil(N / SMs) frames rounded up to a whole pass.  The MMA still runs M = 128, but the
+    // operand tile keeps only a_rows = 32 | 64 | 128 rows per slice in shared memory (the lanes beyond read whatever
+    // follows and are ignored), which leaves room for a deeper codebook ring (d = 512: 2 -> 4 stages).
+    // (Measured and NOT done: 64-frame tiles in two slots for large calls at d = 512, where 128-row tiles leave room for
+    // one slot only.  The update warps serve both slots and their cost per job is mostly fixed latency - re-rank 14 k
+    // cycles for 10 frames as for 21 - so the model default 8 x 1024 x 512 went from 4.94 to 6.00 ms,
+    // profiles/r2u_phase.log.)
+    int tile_rows = TILE_M;
+    if (!dbg_scores && d != 128) {
+        if (N < (long long)num_sms * TILE_M) {
+            const long long per_sm = (N + num_sms - 1) / num_sms;
+            tile_rows = (int)((per_sm + 31) / 32 * 32);
+            if (tile_rows > TILE_M) tile_rows = TILE_M;
+        }
+    }
+    const int a_rows = tile_rows <= 32 ? 32 : (tile_rows <= 64 ? 64 : TILE_M);
+    const SmemPlan sp = plan_smem(d, smem_max, a_rows);
     if (sp.nstage < 2) {
         set_error("rvq_encode: d=%d leaves no room for the codebook ring in %d bytes of shared memory", d, smem_max);
         return RVQ_ERR_ARG;
@@ -1010,16 +1064,6 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
         set_error("rvq_encode: cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
         return RVQ_ERR_CUDA;
     }
-    // Small calls (the reference's training and inference shapes: 136 ... 4000 frames) would fill a handful of SMs with
-    // whole 128-frame tiles and leave the rest idle, while a tile-stage costs the update warps one pass per 32 frames.
-    // Spread them instead: tiles of ceil(N / SMs) frames rounded up to a whole pass.  The MMA still runs M = 128 (the
-    // unused lanes hold zeros); the codebook stream per SM is the same as for a full tile.
-    int tile_rows = TILE_M;
-    if (!dbg_scores && N < (long long)num_sms * TILE_M) {
-        const long long per_sm = (N + num_sms - 1) / num_sms;
-        tile_rows = (int)((per_sm + 31) / 32 * 32);
-        if (tile_rows > TILE_M) tile_rows = TILE_M;
-    }
     const int num_tiles = (int)((N + tile_rows - 1) / tile_rows);
     // persistent grid of whole clusters: as many as the tiles need, at most one CTA per SM
     const int want_clusters = (num_tiles + CL - 1) / CL, max_clusters = num_sms / CL;
@@ -1027,6 +1071,7 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     EncParams p{};
     p.cluster = CL;
     p.tile_rows = tile_rows;
+    p.a_rows = a_rows;
     p.x = x;
     p.N = N;
     p.ad = RowAddrT{L, sb, sl, sd};
