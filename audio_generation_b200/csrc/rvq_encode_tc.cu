@@ -815,7 +815,11 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             const long long ts2 = clock64();
             t_score += ts1 - ts0;
             t_apply += ts2 - ts1;
-            if (sub == 0 && commit_local != 0.0) atomicAdd(&misc->commit_acc[q], commit_local);
+            // (one shared-memory double atomic per warp: they are CAS loops, and 32 lanes on one address were 2 % of the
+            // kernel's stall samples)
+            commit_local += __shfl_xor_sync(0xffffffffu, commit_local, 8);
+            commit_local += __shfl_xor_sync(0xffffffffu, commit_local, 16);
+            if ((u & 31) == 0 && commit_local != 0.0) atomicAdd(&misc->commit_acc[q], commit_local);
             commit_local = 0.0;
             long long t2 = clock64();
             // ---------------- frames the filter could not certify: exact scan of every code

@@ -450,3 +450,42 @@ def test_small_calls_with_partly_filled_tiles_are_bit_identical(d, layout):
     assert torch.equal(idx, idx_e)
     assert torch.equal(m.ema_count, ref.ema_count)
     assert torch.allclose(m.codebooks, ref.codebooks, rtol=1e-5, atol=1e-6)       # float atomics: summation order only
+
+
+def test_prepared_allowance_tables_are_consistent():
+    """K0 (rvq_aux.cu:k0_bound): the byte table bounds the fp32 allowance factor of every code from above
+    (xb_k * U1 >= xc_k), codes at or below the stage's norm cap carry no allowance, the chunk flags mark exactly the
+    chunks that hold one, padding codes none - on a codebook with outliers (cap = lower quartile) and on a freshly
+    initialised one (norms within 25 %: cap = the maximum, no allowance at all)."""
+    nq, K, d = 3, 700, 256
+    Kpad = (K + 255) // 256 * 256
+    for outliers in (True, False):
+        torch.manual_seed(5)
+        m = quantizer(nq, K, d)
+        with torch.no_grad():
+            m.codebooks.copy_(torch.randn(nq, K, d))
+            if outliers:
+                m.codebooks[:, ::17] *= 4.0
+            m.ema_sum.copy_(m.codebooks)
+        m = m.cuda().eval()
+        op, nrm, meta = m._prepared()
+        torch.cuda.synchronize()
+        meta = meta.reshape(nq, 8).cpu()
+        xc = nrm[9 * nq * Kpad:10 * nq * Kpad].reshape(nq, Kpad).cpu()
+        raw = nrm[10 * nq * Kpad:].view(torch.uint8)
+        xb = raw[:nq * Kpad].reshape(nq, Kpad).cpu().float()
+        flag = raw[nq * Kpad:nq * Kpad + 4 * nq * (Kpad // 256)].view(torch.int32).reshape(nq, Kpad // 256).cpu()
+        for q in range(nq):
+            sb, cap, U2, cnmax, U1 = [float(meta[q, i]) for i in (0, 1, 5, 6, 7)]
+            cs = m.codebooks[q].detach().cpu().double().norm(dim=1) * sb
+            large = cs > cap * sb * (1 + 1e-4)
+            small = cs < cap * sb * (1 - 1e-4)
+            assert (xc[q, K:] == 0).all() and (xb[q, K:] == 0).all()
+            assert (xb[q] * U1 >= xc[q]).all()                          # the table is an upper bound ...
+            assert (xb[q] * U1 <= xc[q] + U1 * 2.001).all()             # ... within two units
+            assert (xc[q, :K][small] == 0).all() and (xc[q, :K][large] > 0).all()
+            assert torch.equal(flag[q] != 0, (xc[q].reshape(-1, 256) > 0).any(dim=1))
+            if outliers:
+                assert cap < cnmax * 0.5 and large.sum() >= K // 17     # capped at the live codes' scale
+            else:
+                assert cap == pytest.approx(cnmax, rel=1e-4) and not large.any() and U1 == 0
