@@ -123,7 +123,7 @@ __device__ __forceinline__ void store_a4(uint8_t* smem_a, int row, int c, float4
 template <int NP>
 __device__ __forceinline__ void apply_seg(uint8_t* smem_a, const RTile& rt, int row, const float* __restrict__ cw,
                                           float* __restrict__ ssum, int c0, bool write_a, float sa, float& sq,
-                                          float& amax, uint32_t asb) {
+                                          uint32_t asb) {
     float4 rv[NP], cv[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -144,15 +144,14 @@ __device__ __forceinline__ void apply_seg(uint8_t* smem_a, const RTile& rt, int 
         sq = fmaf(nr.y, nr.y, sq);
         sq = fmaf(nr.z, nr.z, sq);
         sq = fmaf(nr.w, nr.w, sq);
-        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(nr.x), fabsf(nr.y)), fmaxf(fabsf(nr.z), fabsf(nr.w))));
         if (write_a) store_a4(smem_a, row, c, nr, sa, asb);
     }
 }
 
 // An 8-lane group applies one stage to one frame in ONE pass over memory:
 //   r <- r - c_win (fp32, residual tile in the L2-resident scratch), EMA statistics of the stage input,
-//   squared norm / max of the new residual, and the fp16 operand row + row constants of the next stage.
-// The operand scale of the next stage is chosen from the bound max|r'| <= amax_in + max|c| (known before
+//   squared norm of the new residual, and the fp16 operand row + row constants of the next stage.
+// The operand scale of the next stage is chosen from the bound max|r'| <= ||r||_2 + max|c| (known before
 // the pass), so the converted row is written in the same pass; the error bound uses the exact new norm.
 // All 32 lanes of the warp must call this together (8-lane shuffles with a full mask); `active` gates effects.
 //   next_q_abs < 0 : last stage (no operand for a next stage)
@@ -175,8 +174,11 @@ __device__ __forceinline__ StageC load_stage_consts(const EncParams& p, int q_ab
 __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt, int sl,
                                           int row, bool active, bool row_valid, int kwin, int q_abs, int next_q_abs,
                                           int sub, float* sq_out, const StageC& sc) {
+#ifdef RVQ_TC_APPLY_PROF  // build-time experiment switch (RVQ_NVCC_DEFS): splits the apply time of thread 0 into
+    const long long tp0 = clock64();  // prologue / memory pass / reduction + row constants (counters 12-15)
+#endif
     const int d = p.d;
-    float sq = 0.f, amax = 0.f;
+    float sq = 0.f;
     float sa = 0.f;
     const float sb = sc.sb, cnmax = sc.cnmax;
     int a = 0, b = 0;
@@ -189,32 +191,47 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
         sa = exp2i(a);
     }
     const uint32_t asb = (uint32_t)p.a_rows * 128u;
+#ifdef RVQ_TC_APPLY_PROF
+    const long long tp1 = clock64();
+#endif
     if (active) {
         const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d;
         float* ssum = (p.stats_sum && row_valid) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d : nullptr;
         int c0 = sub * 4;
 #pragma unroll 1
         // 256 features per step when possible: one L2 round trip covers eight pieces of the frame and of the code
-        for (; c0 + 256 <= d + sub * 4; c0 += 256) apply_seg<8>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax, asb);
+        for (; c0 + 256 <= d + sub * 4; c0 += 256) apply_seg<8>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, asb);
         if (d & 128) {
-            apply_seg<4>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax, asb);
+            apply_seg<4>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, asb);
             c0 += 128;
         }
-        if (d & 64) apply_seg<2>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, amax, asb);
+        if (d & 64) apply_seg<2>(smem_a, rt, row, cw, ssum, c0, write_a, sa, sq, asb);
     }
+#ifdef RVQ_TC_APPLY_PROF
+    const long long tp2 = clock64();
+#endif
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    }
+    for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if (sq_out) *sq_out = sq;
     if (active && sub == 0) {
-        misc->row_amax[sl][row] = amax;
+        // bound on max|r'| for the next stage's operand scale: ||r'||_2 (as the TMEM kernel does).  The true maximum
+        // cost four FMNMX per 16 bytes on the ALU pipe the scan warps saturate; the scale only has to keep fp16 from
+        // overflowing, its relative precision does not depend on it
+        misc->row_amax[sl][row] = sqrtf(sq) * 1.00002f;
         if (write_a) {
             if (!isfinite(sq)) force_exact = true;
             write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
         }
     }
+#ifdef RVQ_TC_APPLY_PROF
+    if (p.prof && threadIdx.x == UPD_WARP0 * 32) {
+        const long long tp3 = clock64();
+        atomicAdd(p.prof + 12, (unsigned long long)(tp1 - tp0));
+        atomicAdd(p.prof + 13, (unsigned long long)(tp2 - tp1));
+        atomicAdd(p.prof + 14, (unsigned long long)(tp3 - tp2));
+        atomicAdd(p.prof + 15, 1ull);
+    }
+#endif
 }
 
 // Two frames of d = 128 per 8-lane group with every load of both frames issued before the first dependent
