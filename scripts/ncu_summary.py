@@ -18,6 +18,10 @@ KEYS = [
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    # EMA statistics: vector reductions into the L2 (red.global.add.v4.f32)
+    "smsp__inst_executed_op_global_red.sum", "lts__t_sectors_srcunit_tex_op_red.sum",
+    "lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed",
+    "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed",
 ]
 rows = list(csv.reader(sys.stdin))
 hdr, units, vals = rows[0], rows[1], rows[2]
