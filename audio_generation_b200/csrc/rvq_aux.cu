@@ -5,6 +5,8 @@
 //   exact-scan encode (every code scored in fp32 on CUDA cores; verification / RVQ_ALGO_EXACT_SCAN)
 #include <cuda_fp16.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "exact.cuh"
 
@@ -424,6 +426,36 @@ extern "C" int rvq_prepare_codebooks(const float* cb, const int* k_valid, int nq
     return RVQ_OK;
 }
 
+// Stream-ordered scratch for the few floats K3 and the weighted lookup need.  The device's DEFAULT memory pool hands
+// freed memory back to the driver at the next synchronisation (release threshold 0), after which the next
+// cudaMallocAsync maps memory again - the suspected cause of an occasional 0.7-1 ms between the encode kernel and the
+// end of K3 (profiles/r2n_bench_c2.json: collective.k0_k3_ms 0.70 against 0.02-0.03 in the other runs).  An own pool
+// that keeps what it has (threshold = max) makes the allocation a pointer bump either way.
+static cudaError_t scratch_alloc(float** out, size_t bytes, cudaStream_t st) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(out, bytes, st);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            e = cudaMemPoolCreate(&pools[dev], &props);
+            if (e != cudaSuccess) return e;
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool = pools[dev];
+    }
+    return cudaMallocFromPoolAsync(reinterpret_cast<void**>(out), bytes, pool, st);
+}
+
 extern "C" int rvq_ema_finalize(float* cb, float* ema_count, float* ema_sum, const float* stats_sum,
                                 const float* stats_cnt, const int* k_valid, int nq_use, int K, int d, float decay,
                                 float eps, void* stream) {
@@ -435,7 +467,7 @@ extern "C" int rvq_ema_finalize(float* cb, float* ema_count, float* ema_sum, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // n_tot scratch: a small stream-ordered allocation (nq floats)
     float* ntot = nullptr;
-    RVQ_CUDA(cudaMallocAsync(&ntot, sizeof(float) * nq_use, st));
+    RVQ_CUDA(scratch_alloc(&ntot, sizeof(float) * nq_use, st));
     const float omd = (float)(1.0 - (double)decay);
     k3_counts<<<nq_use, 1024, 0, st>>>(ema_count, stats_cnt, k_valid, K, decay, omd, ntot);
     const long long warps = (long long)nq_use * K;
@@ -455,7 +487,7 @@ extern "C" int rvq_ema_counts(float* ema_count, const float* stats_cnt, const in
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* ntot = nullptr;
-    RVQ_CUDA(cudaMallocAsync(&ntot, sizeof(float) * nq_use, st));
+    RVQ_CUDA(scratch_alloc(&ntot, sizeof(float) * nq_use, st));
     const float omd = (float)(1.0 - (double)decay);
     k3_counts<<<nq_use, 1024, 0, st>>>(ema_count, stats_cnt, k_valid, K, decay, omd, ntot);
     RVQ_CUDA(cudaGetLastError());
@@ -475,7 +507,7 @@ extern "C" int rvq_dequantize(const float* cb, const long long* idx, long long N
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float* wdev = nullptr;
     if (w) {
-        RVQ_CUDA(cudaMallocAsync(&wdev, sizeof(float) * nq_use, st));
+        RVQ_CUDA(scratch_alloc(&wdev, sizeof(float) * nq_use, st));
         RVQ_CUDA(cudaMemcpyAsync(wdev, w, sizeof(float) * nq_use, cudaMemcpyHostToDevice, st));
     }
     RowAddr ad{L, stride_b, stride_l, stride_d};
