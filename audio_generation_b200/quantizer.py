@@ -563,11 +563,15 @@ class HostEncoder:
     the device->host copy of chunk i-1 overlap the kernel of chunk i.  This is the call a serving user makes when
     latents arrive from another process; ``bench.py`` times it as the ``e2e`` figure.
 
+    The chunk size trades the pipeline's fill / drain (one chunk's copy in, one chunk's kernel and copy out per call)
+    against per-copy overheads: 65536 frames measured best on C2 (``scripts/e2e_tune.py``, profiles/r2z_e2e_tune.log:
+    103 M frames/s = 53 GB/s of host->device traffic for 1 M frames per call, against 55.6 GB/s for a bare 1 GiB copy).
+
     ``packed=True`` returns the codes in their wire format (``rvq_pack_indices``: ``ceil(n * code_bits / 8)`` bytes per
     frame instead of ``8 n``), which is what crosses PCIe back to the host.
     """
 
-    def __init__(self, quantizer: ResidualQuantizer, chunk_frames: int = 1 << 17, n_buffers: int = 3,
+    def __init__(self, quantizer: ResidualQuantizer, chunk_frames: int = 1 << 16, n_buffers: int = 3,
                  packed: bool = False):
         self.q = quantizer
         self.chunk = int(chunk_frames)

@@ -580,7 +580,7 @@ def main():
                    d2h_bytes_per_step=4, frames_per_step=n_e2e,
                    api="som_quantizer.ResidualQuantizer.forward(update_codebook=True) on host-fed latents")
     if not args.no_e2e and not wl["update"]:
-        n_e2e = min(N, 1 << 19)
+        n_e2e = min(N, 1 << 20)                          # one call = the workload's batch
         xh = torch.randn(n_e2e, d).pin_memory()
         he = HostEncoder(quant.eval(), packed=True)     # codes cross PCIe in their wire format (10 bits per code)
         bpf = he.bytes_per_frame(nq)
