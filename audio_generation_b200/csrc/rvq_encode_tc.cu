@@ -148,6 +148,38 @@ __device__ __forceinline__ void apply_seg(uint8_t* smem_a, const RTile& rt, int 
     }
 }
 
+// The two halves of apply_seg<8> for the software-pipelined apply (d % 256 == 0): the 16 loads of a 256-feature segment,
+// and everything that consumes them.  Inactive frames (exact scan pending) load harmlessly and store nothing; every
+// element of the register arrays is assigned (conditionally initialised arrays are demoted to local memory).
+__device__ __forceinline__ void seg8_load(const RTile& rt, int row, const float* __restrict__ cw, int c0,
+                                          float4 (&rv)[8], float4 (&cv)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        rv[i] = *reinterpret_cast<float4*>(rt.at(row, c0 + i * 32));
+        cv[i] = ldg_nc_v4(cw + c0 + i * 32);
+    }
+}
+__device__ __forceinline__ void seg8_consume(uint8_t* smem_a, const RTile& rt, int row, float* __restrict__ ssum, int c0,
+                                             bool active, bool write_a, float sa, float& sq, uint32_t asb,
+                                             const float4 (&rv)[8], const float4 (&cv)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i * 32;
+        if (ssum) red_add_v4(ssum + c, rv[i]);
+        float4 nr;
+        nr.x = rv[i].x - cv[i].x;
+        nr.y = rv[i].y - cv[i].y;
+        nr.z = rv[i].z - cv[i].z;
+        nr.w = rv[i].w - cv[i].w;
+        if (active) *reinterpret_cast<float4*>(rt.at(row, c)) = nr;
+        sq = fmaf(nr.x, nr.x, sq);
+        sq = fmaf(nr.y, nr.y, sq);
+        sq = fmaf(nr.z, nr.z, sq);
+        sq = fmaf(nr.w, nr.w, sq);
+        if (active && write_a) store_a4(smem_a, row, c, nr, sa, asb);
+    }
+}
+
 // An 8-lane group applies one stage to one frame in ONE pass over memory:
 //   r <- r - c_win (fp32, residual tile in the L2-resident scratch), EMA statistics of the stage input,
 //   squared norm of the new residual, and the fp16 operand row + row constants of the next stage.
@@ -232,98 +264,6 @@ __device__ __forceinline__ void apply_row(const EncParams& p, Misc* misc, uint8_
         atomicAdd(p.prof + 15, 1ull);
     }
 #endif
-}
-
-// Two frames of d = 128 per 8-lane group with every load of both frames issued before the first dependent
-// instruction (one L2 round trip per pair of frames).  Inactive frames (exact-scan fallback pending) load
-// harmlessly and store nothing.  The bound on max|r'| that picks the next operand scale is ||r||_2 + max|c|.
-__device__ __forceinline__ void apply_two_rows_128(const EncParams& p, Misc* misc, uint8_t* smem_a, const RTile& rt,
-                                                   int sl, int row0, int row1, bool act0, bool act1, bool val0,
-                                                   bool val1, int kw0, int kw1, int q_abs, int next_q_abs, int sub,
-                                                   float& sq0_out, float& sq1_out) {
-    constexpr int d = 128;
-    const bool write_a = next_q_abs >= 0;
-    float sb = 1.f, cnmax = 0.f, cmax_q = 0.f;
-    int b = 0;
-    if (write_a) {
-        const float* mq = p.cb_meta + (size_t)next_q_abs * META_STRIDE;
-        sb = mq[0];
-        cnmax = mq[1];
-        b = ilog2f_floor(sb);
-        cmax_q = p.cb_meta[(size_t)q_abs * META_STRIDE + 2];
-    }
-    float* rr0 = rt.at(row0, sub * 4);
-    float* rr1 = rt.at(row1, sub * 4);
-    const float* cw0 = p.cb + ((size_t)q_abs * p.K + kw0) * d + sub * 4;
-    const float* cw1 = p.cb + ((size_t)q_abs * p.K + kw1) * d + sub * 4;
-    float4 r0[4], r1[4], c0[4], c1[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r0[i] = *reinterpret_cast<const float4*>(rr0 + i * 32);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) r1[i] = *reinterpret_cast<const float4*>(rr1 + i * 32);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c0[i] = ldg_nc_v4(cw0 + i * 32);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c1[i] = ldg_nc_v4(cw1 + i * 32);
-    // A-tile address pieces: feature c = sub*4 + i*32 -> slice i>>1, 16-byte chunk (sub>>1) + (i&1)*4 (xor row&7)
-    const uint32_t s1 = (uint32_t)sub >> 1, s0 = ((uint32_t)sub & 1u) << 3;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int row = j ? row1 : row0;
-        const bool active = j ? act1 : act0;
-        const bool valid = j ? val1 : val0;
-        const int kwin = j ? kw1 : kw0;
-        float* rrow = j ? rr1 : rr0;
-        int a = 0;
-        float sa = 0.f;
-        bool force_exact = false;
-        if (write_a) {
-            a = pick_row_exp(misc->row_amax[sl][row] + cmax_q, b, force_exact);
-            sa = exp2i(a);
-        }
-        float sq = 0.f;
-        float* ssum = (p.stats_sum && valid && active) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d + sub * 4
-                                                       : nullptr;
-        uint8_t* arow = smem_a + (uint32_t)row * 128u + s0;
-        const uint32_t rx = (uint32_t)row & 7u;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 rv = j ? r1[i] : r0[i];
-            const float4 cv = j ? c1[i] : c0[i];
-            if (ssum) red_add_v4(ssum + i * 32, rv);
-            float4 nr;
-            nr.x = rv.x - cv.x;
-            nr.y = rv.y - cv.y;
-            nr.z = rv.z - cv.z;
-            nr.w = rv.w - cv.w;
-            sq = fmaf(nr.x, nr.x, sq);
-            sq = fmaf(nr.y, nr.y, sq);
-            sq = fmaf(nr.z, nr.z, sq);
-            sq = fmaf(nr.w, nr.w, sq);
-            if (active) {
-                *reinterpret_cast<float4*>(rrow + i * 32) = nr;
-                if (write_a) {
-                    const __half2 h01 = __floats2half2_rn(nr.x * sa, nr.y * sa);
-                    const __half2 h23 = __floats2half2_rn(nr.z * sa, nr.w * sa);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<const uint32_t*>(&h01);
-                    pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-                    *reinterpret_cast<uint2*>(arow + (uint32_t)(i >> 1) * A_SLICE_BYTES +
-                                              (((s1 + (uint32_t)(i & 1) * 4u) ^ rx) << 4)) = pk;
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (j) sq1_out = sq; else sq0_out = sq;
-        if (active && sub == 0) {
-            misc->row_amax[sl][row] = sqrtf(sq) * 1.00002f;   // ||r'||_2 >= max|r'|
-            if (write_a) {
-                if (!isfinite(sq)) force_exact = true;
-                write_row_consts(p, misc, sl, row, d, sq, force_exact, a, b, sb, cnmax);
-            }
-        }
-    }
 }
 
 // Stage-0 initialisation of one frame by an 8-lane group: x -> residual scratch, exact max -> operand scale,
@@ -654,7 +594,7 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
 
         // rows the update passes walk (whole passes of 32 frames; the rest of the 128 lanes stays zero)
         const int tile_rows = p.tile_rows;
-        const int rows_eff = d == 128 ? (tile_rows + 63) & ~63 : (tile_rows + ROWS_PER_PASS - 1) & ~(ROWS_PER_PASS - 1);
+        const int rows_eff = (tile_rows + ROWS_PER_PASS - 1) & ~(ROWS_PER_PASS - 1);
         auto rtile = [&](int sl) {
             RTile rt;
             rt.base = p.r_scratch + ((size_t)blockIdx.x * 2 + sl) * TILE_M * p.r_pitch;
@@ -807,17 +747,58 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                     if (p.stats_cnt) atomicAdd(p.stats_cnt + (size_t)q_abs * p.K + kwin, 1.f);
                 }
             };
-            if (d == 128) {
+            if ((d & 255) == 0) {
+                // Software-pipelined passes: the loads of the NEXT frame's first segment are issued before the reduction,
+                // row constants and index / statistics writes of the current frame, so that one memory round trip per
+                // pass overlaps ~1.3 k cycles of dependent work instead of following it (profiles/r2z_apply_split.log:
+                // loads 1.2 k, the rest 2.5 k cycles of a pass).  Same arithmetic in the same order as apply_row.
+                const bool write_a = next_q_abs >= 0;
+                const uint32_t asb = (uint32_t)p.a_rows * 128u;
+                const int b_exp = write_a ? ilog2f_floor(sc.sb) : 0;
+                float4 rv[8], cv[8];
+                int row = slot16;
+                bool active = misc->win[sl][row] >= 0;
+                int kwin = active ? misc->win[sl][row] : 0;
+                const float* cw = p.cb + ((size_t)q_abs * p.K + kwin) * d;
+                seg8_load(rt, row, cw, sub * 4, rv, cv);
 #pragma unroll 1
-                for (int r0 = slot16; r0 < rows_eff; r0 += 2 * ROWS_PER_PASS) {
-                    const int r1 = r0 + ROWS_PER_PASS;
-                    const bool a0 = misc->win[sl][r0] >= 0, a1 = misc->win[sl][r1] >= 0;
-                    const int k0 = a0 ? misc->win[sl][r0] : 0, k1 = a1 ? misc->win[sl][r1] : 0;
-                    float sq0, sq1;
-                    apply_two_rows_128(p, misc, a_tile, rt, sl, r0, r1, a0, a1, frame_ok(r0), frame_ok(r1), k0, k1,
-                                       q_abs, next_q_abs, sub, sq0, sq1);
-                    post_row(r0, a0, k0, sq0);
-                    post_row(r1, a1, k1, sq1);
+                for (; row < rows_eff; row += ROWS_PER_PASS) {
+                    // operand scale of this frame's next stage (from a bound known before the pass)
+                    bool force_exact = false;
+                    int a_exp = 0;
+                    float sa = 0.f;
+                    if (write_a) {
+                        a_exp = pick_row_exp(misc->row_amax[sl][row] + sc.cmax_q, b_exp, force_exact);
+                        sa = exp2i(a_exp);
+                    }
+                    const bool ok = frame_ok(row);
+                    float* ssum = (active && p.stats_sum && ok) ? p.stats_sum + ((size_t)q_abs * p.K + kwin) * d : nullptr;
+                    float sq = 0.f;
+                    seg8_consume(a_tile, rt, row, ssum, sub * 4, active, write_a, sa, sq, asb, rv, cv);
+                    for (int c0 = sub * 4 + 256; c0 < d; c0 += 256) {
+                        seg8_load(rt, row, cw, c0, rv, cv);
+                        seg8_consume(a_tile, rt, row, ssum, c0, active, write_a, sa, sq, asb, rv, cv);
+                    }
+                    // next frame: its loads fly while this frame is finished
+                    const int nrow = row + ROWS_PER_PASS;
+                    const bool cur_active = active;
+                    const int cur_kwin = kwin;
+                    if (nrow < rows_eff) {
+                        active = misc->win[sl][nrow] >= 0;
+                        kwin = active ? misc->win[sl][nrow] : 0;
+                        cw = p.cb + ((size_t)q_abs * p.K + kwin) * d;
+                        seg8_load(rt, nrow, cw, sub * 4, rv, cv);
+                    }
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (cur_active && sub == 0) {
+                        misc->row_amax[sl][row] = sqrtf(sq) * 1.00002f;
+                        if (write_a) {
+                            if (!isfinite(sq)) force_exact = true;
+                            write_row_consts(p, misc, sl, row, d, sq, force_exact, a_exp, b_exp, sc.sb, sc.cnmax);
+                        }
+                    }
+                    post_row(row, cur_active, cur_kwin, sq);
                 }
             } else {
 #pragma unroll 1
@@ -1052,7 +1033,7 @@ int rvq_launch_tc(const float* x, long long N, long long L, long long sb, long l
     // cycles for 10 frames as for 21 - so the model default 8 x 1024 x 512 went from 4.94 to 6.00 ms,
     // profiles/r2u_phase.log.)
     int tile_rows = TILE_M;
-    if (!dbg_scores && d != 128) {
+    if (!dbg_scores) {
         if (N < (long long)num_sms * TILE_M) {
             const long long per_sm = (N + num_sms - 1) / num_sms;
             tile_rows = (int)((per_sm + 31) / 32 * 32);
