@@ -85,6 +85,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout=10.0):
+        """Block until the first sample has arrived (nvidia-smi needs 1-2 s to start on an 8-GPU box; a timed region
+        that ends before that would have no clocks at all)."""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.05)
+
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
@@ -97,7 +104,12 @@ class ClockSampler:
             return [None] * len(gpus)
         time.sleep(0.15)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15]
+        if not rows and self.rows:
+            # no sample inside the region (shorter than the sampling period): the ones closest to it in time
+            mid = 0.5 * (t0 + t1)
+            tmin = min(abs(t - mid) for (t, _) in self.rows)
+            rows = [r for (t, r) in self.rows if abs(t - mid) <= tmin + 0.06]
         out = []
         for gidx in gpus:
             sm, mx, pw, reasons = [], [], [], set()
@@ -430,6 +442,7 @@ def run_c5(args, wl, rank, world, local, dev):
     sampler = ClockSampler()
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
 
     def step():
         with torch.no_grad():
@@ -534,6 +547,7 @@ def main():
     sampler = ClockSampler()
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
     r = timed_steps(quant, x, wl, args.steps, args.warmup, rank, world, dev)
     ms, kernel_ms, n_warm = r["ms"], r["kernel_ms"], r["n_warm"]
     clocks = None
