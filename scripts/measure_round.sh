@@ -25,6 +25,12 @@ ncu --set full --import-source on --clock-control none -k regex:rvq_encode_tc --
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $out/${tag}_launches_c3.csv \
     python bench.py --workload c3 --steps 3 --warmup 3 --no-cpu --no-e2e > $out/${tag}_ncu_launch_c3.log 2>&1
 for w in c2 c3; do python scripts/phase_profile.py $w >> $out/${tag}_phase_profile.log 2>&1; done
+# row-major frames vs the reference's (B, d, L) storage; the reference's small call shapes; the codebook state 1 / 8
+# shards converge to; bare pinned-copy rate of the box
+python scripts/layout_time.py > $out/${tag}_layout_time.log 2>&1
+python scripts/small_call_profile.py > $out/${tag}_small_profile.log 2>&1
+python scripts/c3_shards_probe.py 1 8 > $out/${tag}_shards_probe.log 2>&1
+python scripts/h2d_ceiling.py > $out/${tag}_h2d_ceiling.log 2>&1
 tail -2 $out/${tag}_bench.err
 for f in c2 c2_frame_kernel c3 c3m c4s c5q reference_cpu; do python - <<PY
 import json
