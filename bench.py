@@ -499,6 +499,9 @@ def main():
     ap.add_argument("--no-latency", action="store_true", help="skip the small-call latency leg")
     ap.add_argument("--algo", default="tensor")
     ap.add_argument("--kernel", default="auto", help="auto | tmem | generic | frame (cross-check kernels)")
+    ap.add_argument("--layout", default="rows", choices=["rows", "bdl"],
+                    help="rows: frames [N, d] (default); bdl: the reference's '(B, d, L) -> b l c' view with L = 512 "
+                         "(vae.py:313), device-resident legs only")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.frames:
@@ -540,7 +543,13 @@ def main():
 
     quant = build_quantizer(wl, dev, args)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.randn(N, d, device=dev, generator=g)
+    if args.layout == "bdl":
+        # the reference's boundary layout: a (B, L, d) VIEW of (B, d, L) storage, features strided by L
+        x = torch.randn(max(N // 512, 1), d, 512, device=dev, generator=g).permute(0, 2, 1)
+        N = x.shape[0] * x.shape[1]
+        args.no_e2e = True
+    else:
+        x = torch.randn(N, d, device=dev, generator=g)
     # the clock sampler (nvidia-smi -lms) starts BEFORE the warm-up: its start-up (NVML initialisation) was seen to
     # stall kernel launches for tens of milliseconds when it fell into the timed region; rows are filtered by time.
     # One sampler per rank, each on its own GPU.
@@ -693,6 +702,7 @@ def main():
                config=dict(workload=args.workload, desc=wl["desc"], nq=nq, K=K, d=d, frames_per_gpu=N,
                            update_codebook=wl["update"], parallelism=f"frames sharded x{world}, codebooks replicated",
                            l2="inputs (%.0f MB) larger than L2; no explicit flush" % (N * d * 4 / 1e6), algo=args.algo,
+                           layout=args.layout,
                            kernel=args.kernel),
                roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=args.steps * launches_per_step,
                clocks=clocks, collective=collective, latency=latency)
