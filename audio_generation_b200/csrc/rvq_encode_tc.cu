@@ -617,21 +617,23 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
             uint8_t* a_tile = smem + (size_t)sl * a_tile_bytes;
             const long long n0 = (long long)tile * tile_rows;
             if (!row_major) {
-                // The reference's (B, d, L) storage: frames are the fastest axis.  A warp takes 32 frames x 8 features:
-                // lane = frame (coalesced 128-byte reads per feature), the eight loads of a lane are independent (one
-                // memory round trip per unit), and they leave as two 16-byte stores into the lane's residual row.
-                const int nrb = rows_eff / 32, units = nrb * (d / 8);
+                // The reference's (B, d, L) storage: frames are the fastest axis.  A warp takes 32 frames x 32 features:
+                // lane = frame (coalesced 128-byte reads per feature), the 32 loads of a lane are independent (one
+                // memory round trip per unit, as many round trips per tile as the row-major load needs), and they leave
+                // as eight 16-byte stores into the lane's residual row.
+                const int nrb = rows_eff / 32, units = nrb * (d / 32);
 #pragma unroll 1
                 for (int unit = uwarp; unit < units; unit += UPD_WARPS) {
-                    const int row = (unit % nrb) * 32 + (u & 31), c0 = (unit / nrb) * 8;
+                    const int row = (unit % nrb) * 32 + (u & 31), c0 = (unit / nrb) * 32;
                     const long long n = n0 + row;
                     const bool ok = row < tile_rows && n < p.N;
                     const float* xr = p.x + (ok ? p.ad.row(n) : 0) + (long long)c0 * p.ad.sd;
-                    float v[8];
+                    float v[32];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = ok ? __ldcs(xr + (long long)j * p.ad.sd) : 0.f;
-                    *reinterpret_cast<float4*>(rt.at(row, c0)) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(rt.at(row, c0 + 4)) = make_float4(v[4], v[5], v[6], v[7]);
+                    for (int j = 0; j < 32; ++j) v[j] = ok ? __ldcs(xr + (long long)j * p.ad.sd) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(rt.at(row, c0 + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
                 named_bar_sync(BAR_UPD, UPD_THREADS);
             }
@@ -909,21 +911,27 @@ rvq_encode_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const EncParams
                         }
                     }
                 } else {
-                    // frames-fastest storage: the same 32 frames x 8 features units as the tile load
-                    const int nrb = rows_eff / 32, units = nrb * (d / 8);
+                    // frames-fastest storage: 32 frames x 16 features per unit (16 loads of x and four 16-byte loads of
+                    // the residual per lane in flight, then the stores)
+                    const int nrb = rows_eff / 32, units = nrb * (d / 16);
 #pragma unroll 1
                     for (int unit = uwarp; unit < units; unit += UPD_WARPS) {
-                        const int row = (unit % nrb) * 32 + (u & 31), c0 = (unit / nrb) * 8;
+                        const int row = (unit % nrb) * 32 + (u & 31), c0 = (unit / nrb) * 16;
                         if (frame_ok(row)) {
                             const long long off = p.ad.row(n0 + row) + (long long)c0 * p.ad.sd;
-                            const float4 ra = *reinterpret_cast<const float4*>(rt.at(row, c0));
-                            const float4 rb = *reinterpret_cast<const float4*>(rt.at(row, c0 + 4));
-                            const float r8[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-                            float v[8];
+                            float4 r4[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = __ldcs(p.x + off + (long long)j * p.ad.sd);
+                            for (int j = 0; j < 4; ++j) r4[j] = *reinterpret_cast<const float4*>(rt.at(row, c0 + 4 * j));
+                            float v[16];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) __stcs(p.xq + off + (long long)j * p.ad.sd, v[j] - r8[j]);
+                            for (int j = 0; j < 16; ++j) v[j] = __ldcs(p.x + off + (long long)j * p.ad.sd);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __stcs(p.xq + off + (long long)(4 * j + 0) * p.ad.sd, v[4 * j + 0] - r4[j].x);
+                                __stcs(p.xq + off + (long long)(4 * j + 1) * p.ad.sd, v[4 * j + 1] - r4[j].y);
+                                __stcs(p.xq + off + (long long)(4 * j + 2) * p.ad.sd, v[4 * j + 2] - r4[j].z);
+                                __stcs(p.xq + off + (long long)(4 * j + 3) * p.ad.sd, v[4 * j + 3] - r4[j].w);
+                            }
                         }
                     }
                 }
