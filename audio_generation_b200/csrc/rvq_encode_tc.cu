@@ -2,21 +2,25 @@
 // sm_100a kernel.  Replaces the per-stage {distance, argmin, gather, subtract, EMA statistics} loop of
 // som_quantizer.ResidualQuantizer.forward (called at /root/reference/networks/vae.py:315-318).
 //
-// Per CTA (one per SM, persistent over 128-frame tiles), per stage q:
+// Per CTA (one per SM, persistent over tiles of up to 128 frames, two tiles in flight while shared memory allows),
+// per stage q:
 //   filter   scores~[128 x K] = (2^a r) . (-2 * 2^b C_q)^T on tcgen05 (fp16 operands, fp32 accumulate in
 //            TMEM, 256 codes per accumulator buffer, two buffers), B streamed by TMA through an mbarrier ring;
 //            the residual operand A is produced by the CTA itself in the UMMA SWIZZLE_128B K-major layout.
-//   argmin   epilogue warps read the accumulators with tcgen05.ld, add 2^(a-b) * (2^(2b)||c||^2) and keep the
-//            three smallest packed (score | column) values per frame; nothing N x K ever reaches HBM.
-//   certify  every code whose approximate score is within delta = 2 * (proven fp16 error bound) of the best is
-//            re-scored exactly in fp32 (exact.cuh); if the third best is also inside delta the frame falls
-//            back to an exact scan of all K codes.  The selected index is therefore the exact fp32 argmin.
-//   update   r <- r - C_q[k] in fp32 (residual tile resident in shared memory for d <= 128, else in an
-//            L2-resident per-CTA scratch), EMA statistics by red.global.add.v4.f32, commit-loss partials,
-//            next stage's fp16 operand written back into the A tile.
+//   argmin   scan warps read the accumulators with tcgen05.ld, add 2^(a-b) * (2^(2b)||c||^2) (minus the allowance
+//            of codes above the stage's norm cap) and keep a two-dimensional running minimum per frame: the minimum
+//            of each of the 16 score columns and the three smallest load minima (encode_common.cuh); nothing
+//            N x K ever reaches HBM.
+//   certify  every code whose approximate score is within the proven error bound of the best
+//            is re-scored exactly in fp32 (exact.cuh), by candidate pairs; if a fourth load is in reach the frame's
+//            columns in reach are scanned exactly.  The selected index is therefore the exact fp32 argmin.
+//   update   r <- r - C_q[k] in fp32 (residual tile in an L2-resident per-CTA scratch), EMA statistics by
+//            red.global.add.v4.f32, commit-loss partials, next stage's fp16 operand written back into the A tile;
+//            software-pipelined passes of 32 frames, 8 lanes per frame.
 //
-// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 / 8-11 = epilogue groups 0 / 1 (accumulator buffers 0 / 1).
+// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = two scan
+// groups (accumulator buffers 0 / 1), warps 12-19 = update warps (both tile slots).  Small calls run partly filled
+// tiles over more SMs (tile_rows / a_rows, rvq_launch_tc).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
