@@ -109,7 +109,7 @@ class ClockSampler:
             # no sample inside the region (shorter than the sampling period): the ones closest to it in time
             mid = 0.5 * (t0 + t1)
             tmin = min(abs(t - mid) for (t, _) in self.rows)
-            rows = [r for (t, r) in self.rows if abs(t - mid) <= tmin + 0.06]
+            rows = [r for (t, r) in self.rows if abs(t - mid) <= tmin + 0.03]   # (the rows of one poll arrive together)
         out = []
         for gidx in gpus:
             sm, mx, pw, reasons = [], [], [], set()

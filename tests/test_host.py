@@ -149,3 +149,24 @@ def test_module_survives_pickle_and_deepcopy():
         c._steps_host = 3
         c.load_state_dict(m.state_dict())
         assert c._steps_host is None and int(c.update_steps) == 9
+
+
+def test_clock_sampler_window_picks_samples_in_or_nearest_to_the_region():
+    """bench.ClockSampler.window: samples inside the timed region (with its tolerance) when there are any, else the
+    samples nearest to it - never an empty answer once the sampler has produced a row (an 8-GPU bench line once came
+    back without clocks because the first sample arrived after a 75 ms region)."""
+    import bench
+
+    s = bench.ClockSampler()
+    s.proc = object()                      # "running": window() only reads self.rows
+    row = "{g}, {mhz}, 1965, 300.0, Not Active, Not Active, Not Active, {cap}"
+    s.rows = [(100.00, row.format(g=0, mhz=1000, cap="Not Active")), (100.00, row.format(g=1, mhz=1100, cap="Not Active")),
+              (100.50, row.format(g=0, mhz=1900, cap="Active")), (100.50, row.format(g=1, mhz=1800, cap="Not Active")),
+              (101.00, row.format(g=0, mhz=1200, cap="Not Active")), (101.00, row.format(g=1, mhz=1300, cap="Not Active"))]
+    inside = s.window(100.45, 100.55, [0, 1])
+    assert inside[0]["sm_mhz"] == 1900 and inside[0]["reasons"] == ["sw_power_cap"] and inside[1]["sm_mhz"] == 1800
+    nearest = s.window(100.70, 100.75, [0, 1])          # no sample inside: the closest ones (t = 100.5) are used
+    assert nearest[0]["sm_mhz"] == 1900 and nearest[0]["samples"] == 1
+    assert s.window(100.7, 100.75, [2]) == [None]        # a GPU the sampler never saw
+    s.rows = []
+    assert s.window(0.0, 1.0, [0]) == [None]
