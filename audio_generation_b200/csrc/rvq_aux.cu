@@ -131,7 +131,9 @@ __global__ void k0_convert(const float* __restrict__ cb, int nq, int K, int Kpad
 // The cap is the stage's lower-quartile norm (cs_max itself when the norms are concentrated, max <= 1.25 x quartile:
 // freshly initialised codebooks - no code is flagged and the generic kernel's epilogue stays on its short path).
 // Measured on C3 (profiles/r2g_probe_*.log, encode kernel with statistics after 150 updates, 1 / 8 shards' state):
-// cap 1.5 x p25 14.66 / 15.41 ms, cap p25 13.86 / 14.72 ms (16.13 / 19.07 ms with the stage maximum).
+// cap 1.5 x p25 14.66 / 15.41 ms, cap p25 13.86 / 14.72 ms (16.13 / 19.07 ms with the stage maximum).  Once the
+// allowances are per code, WHICH low quantile is the cap no longer matters: p10 / p25 / p50 give 12.89 / 12.89 / 12.92 ms
+// on the final kernel (profiles/r3j_cap_quantile.log).
 #ifndef RVQ_CAP_DIV
 #define RVQ_CAP_DIV 4
 #endif
